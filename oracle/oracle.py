@@ -1,0 +1,227 @@
+"""ctypes binding of the CPU oracle (oracle/nbody_oracle.c) and of the
+reference-kernel harness (oracle/_ref/libnbody_gpuref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package never
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "libnbody_oracle.so"
+GPUREF_SO = HERE / "_ref" / "libnbody_gpuref.so"
+
+COVERAGE_REFERENCE = 0
+COVERAGE_FULL = 1
+EV_ABSORB = 0
+EV_KILLED = 1
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("growth", C.c_float), ("field_w", C.c_int),
+                ("field_h", C.c_int), ("coverage", C.c_int), ("threads", C.c_int)]
+
+
+class OrcCov(C.Structure):
+    _fields_ = [("n", C.c_int), ("blocks", C.c_int), ("limit_last", C.c_int), ("n_active", C.c_int)]
+
+
+class OrcRng(C.Structure):
+    _fields_ = [("u", C.c_uint64), ("v", C.c_uint64), ("w", C.c_uint64)]
+
+
+EVENT_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("kind", np.int32)])
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (always) and, when /root/reference is present,
+    the reference-kernel harness.  Building the checker is not using it."""
+    src = HERE / "nbody_oracle.c"
+    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
+    ref_root = Path(os.environ.get("NBODY_REFERENCE", "/root/reference"))
+    if (ref_root / "src" / "nbody.cu").exists():
+        harness = HERE / "gpu_ref_harness.cu"
+        if force or not GPUREF_SO.exists() or GPUREF_SO.stat().st_mtime < harness.stat().st_mtime:
+            subprocess.run(["make", "-C", str(HERE), "ref", f"REFERENCE={ref_root}"],
+                           check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(ORACLE_SO))
+        fp = C.POINTER(C.c_float)
+        L.orc_rng_seed.argtypes = [C.POINTER(OrcRng), C.c_uint64]
+        L.orc_rng_ival64.argtypes = [C.POINTER(OrcRng)]
+        L.orc_rng_ival64.restype = C.c_uint64
+        L.orc_rng_fval.argtypes = [C.POINTER(OrcRng)]
+        L.orc_rng_fval.restype = C.c_double
+        L.orc_init_square.argtypes = [fp, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_float, C.c_float]
+        L.orc_coverage.argtypes = [C.c_int, C.c_int, C.POINTER(OrcCov)]
+        L.orc_rows.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
+                               fp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+        L.orc_step.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.c_void_p, C.c_longlong,
+                               C.POINTER(C.c_longlong)]
+        L.orc_step.restype = C.c_int
+        L.orc_fnv1a64.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
+        L.orc_fnv1a64.restype = C.c_uint64
+        L.orc_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _fptr(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def params(dt=0.2, growth=0.1, field_w=100000, field_h=100000, coverage=COVERAGE_REFERENCE, threads=0):
+    return OrcParams(np.float32(dt), np.float32(growth), int(field_w), int(field_h), int(coverage), int(threads))
+
+
+def coverage(n: int, mode: int) -> dict:
+    c = OrcCov()
+    lib().orc_coverage(n, mode, C.byref(c))
+    return {"n": c.n, "blocks": c.blocks, "limit_last": c.limit_last, "n_active": c.n_active}
+
+
+def rng_stream(seed: int, count: int):
+    g = OrcRng()
+    lib().orc_rng_seed(C.byref(g), seed)
+    return [lib().orc_rng_ival64(C.byref(g)) for _ in range(count)]
+
+
+def rng_fvals(seed: int, count: int):
+    g = OrcRng()
+    lib().orc_rng_seed(C.byref(g), seed)
+    return [lib().orc_rng_fval(C.byref(g)) for _ in range(count)]
+
+
+def init_square(n, seed=1024, field_w=100000, field_h=100000, min_mass=1e4, max_mass=1e17,
+                min_radius=50.0, max_radius=200.0) -> np.ndarray:
+    """BodiesData block (6*n float32): pos[n][2], vel[n][2], mass[n], radius[n]."""
+    block = np.zeros(6 * n, dtype=np.float32)
+    lib().orc_init_square(_fptr(block), n, seed, field_w, field_h,
+                          np.float32(min_mass), np.float32(max_mass),
+                          np.float32(min_radius), np.float32(max_radius))
+    return block
+
+
+def split(block: np.ndarray, n: int):
+    """Views (pos[n,2], vel[n,2], mass[n], radius[n]) of a BodiesData block."""
+    return (block[:2 * n].reshape(n, 2), block[2 * n:4 * n].reshape(n, 2),
+            block[4 * n:5 * n], block[5 * n:6 * n])
+
+
+def step(block: np.ndarray, n: int, par: OrcParams, want_events: bool = False):
+    """One step in place.  Returns (new_n, stats dict, events or None)."""
+    stats = (C.c_longlong * 3)()
+    ev = None
+    if want_events:
+        cap = max(16, 8 * n)
+        while True:
+            work = block[:6 * n].copy()
+            ev = np.zeros(cap, dtype=EVENT_DTYPE)
+            new_n = lib().orc_step(_fptr(work), n, C.byref(par), ev.ctypes.data, cap, stats)
+            if stats[1] <= cap:
+                block[:6 * n] = work
+                ev = ev[:stats[1]]
+                break
+            cap = int(stats[1])
+    else:
+        new_n = lib().orc_step(_fptr(block), n, C.byref(par), None, 0, stats)
+    return new_n, {"pairs": int(stats[0]), "events": int(stats[1]), "asserts": int(stats[2])}, ev
+
+
+def rows(block: np.ndarray, n: int, par: OrcParams, row_idx):
+    """Post-step (vx, vy, px, py, m, r) of selected rows; returns (out[nrows,6], hits, visited)."""
+    idx = np.ascontiguousarray(row_idx, dtype=np.int32)
+    out = np.zeros((len(idx), 6), dtype=np.float32)
+    hits = np.zeros(len(idx), dtype=np.int32)
+    visited = np.zeros(len(idx), dtype=np.int64)
+    lib().orc_rows(_fptr(block), n, C.byref(par), idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx),
+                   _fptr(out.reshape(-1)), hits.ctypes.data_as(C.POINTER(C.c_int)),
+                   visited.ctypes.data_as(C.POINTER(C.c_longlong)))
+    return out, hits, visited
+
+
+def fnv(a: np.ndarray, h: int = 0) -> int:
+    a = np.ascontiguousarray(a)
+    return int(lib().orc_fnv1a64(a.ctypes.data, a.nbytes, h))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+# ---------------------------------------------------------------------------
+# Reference kernels (GPU only): oracle/_ref/libnbody_gpuref.so
+# ---------------------------------------------------------------------------
+_gref = None
+
+
+def gpuref_available() -> bool:
+    return GPUREF_SO.exists()
+
+
+def gpuref() -> C.CDLL:
+    global _gref
+    if _gref is None:
+        G = C.CDLL(str(GPUREF_SO))
+        fp = C.POINTER(C.c_float)
+        G.gpuref_open.argtypes = [fp, C.c_int]
+        G.gpuref_read.argtypes = [fp]
+        G.gpuref_step.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, fp]
+        G.gpuref_time_kernels.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, fp]
+        G.gpuref_main_in.argtypes = [C.c_char_p]
+        _gref = G
+    return _gref
+
+
+class GpuRef:
+    """The unmodified reference kernels driven step by step (needs a GPU)."""
+
+    def __init__(self, block: np.ndarray, n: int):
+        rc = gpuref().gpuref_open(_fptr(np.ascontiguousarray(block[:6 * n])), n)
+        if rc != 0:
+            raise RuntimeError(f"gpuref_open failed: {rc}")
+
+    def step(self, par: OrcParams):
+        ms = C.c_float(0)
+        n = gpuref().gpuref_step(par.dt, par.growth, par.field_w, par.field_h, C.byref(ms))
+        if n < 0:
+            raise RuntimeError(f"gpuref_step failed: {n}")
+        return n, float(ms.value)
+
+    def read(self):
+        n = gpuref().gpuref_n()
+        block = np.zeros(6 * max(n, 1), dtype=np.float32)
+        if n > 0:
+            gpuref().gpuref_read(_fptr(block))
+        return block[:6 * max(n, 0)], n
+
+    def close(self):
+        gpuref().gpuref_close()
+
+
+def gpuref_time_kernels(block, n, par: OrcParams, warmup=1, reps=3) -> float:
+    ms = C.c_float(0)
+    rc = gpuref().gpuref_time_kernels(_fptr(np.ascontiguousarray(block[:6 * n])), n, par.dt, par.growth,
+                                      par.field_w, par.field_h, warmup, reps, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"gpuref_time_kernels failed: {rc}")
+    return float(ms.value) / reps
