@@ -1,0 +1,206 @@
+/*
+ * nbody_b200.h -- C ABI of the B200-native ppa-nbody-collisions time step.
+ *
+ * The reference (Aidan900/ppa-nbody-collisions) has no plugin/FFI layer: its
+ * only boundary is the body of main()'s loop in src/nbody.cu:460-545, the two
+ * kernel signatures it launches (ComputeForces src/nbody.cu:139-140,
+ * MoveBodies src/nbody.cu:277-278) and the contiguous BodiesData block they
+ * share (src/nbody.cu:47-124).  This header is that boundary turned into a
+ * C-callable library: plain pointers and sizes, no C++ or torch types, every
+ * entry point returns 0 or a negative NB_ERR_* code and never throws.
+ *
+ * One context owns one GPU (one process per GPU when sharded).  The context
+ * owns all device memory; the caller owns every host buffer.  A context is not
+ * re-entrant: one host thread at a time.
+ *
+ * There is NO CPU fallback: nb_create() fails with NB_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_VERSION 100
+
+/* error codes */
+#define NB_OK 0
+#define NB_ERR_INVALID (-1)           /* bad argument                                   */
+#define NB_ERR_CUDA (-2)              /* CUDA runtime / driver error (see nb_last_error) */
+#define NB_ERR_CAPACITY (-3)          /* n exceeds n_max, or host buffer too small      */
+#define NB_ERR_CANDIDATE_OVERFLOW (-4)/* collision overflow list was too small          */
+#define NB_ERR_COMM (-5)              /* NCCL error or communicator not initialised     */
+#define NB_ERR_IO (-6)                /* file could not be read / written               */
+#define NB_ERR_EVENT_OVERFLOW (-7)    /* event log was too small (events were dropped)  */
+
+/* coverage: which ordered pairs (i, j) a step evaluates */
+#define NB_COVERAGE_REFERENCE 0       /* exactly the pairs src/nbody.cu:182-207 visits (floor(n/128)
+                                         blocks, last j-tile truncated to n % 129, frozen tail)      */
+#define NB_COVERAGE_FULL 1            /* true all-pairs: every i against every j != i               */
+
+/* event kinds (the reference emits none; they are derived from src/nbody.cu:215-226) */
+#define NB_EV_ABSORB 0                /* thread i saw a hit with m_i >= m_j: i gains m_j, growth*r_j */
+#define NB_EV_KILLED 1                /* thread i saw a hit with m_i <  m_j: i's mass becomes 0      */
+
+#define NB_GRAV_CONSTANT 6.67408e-11f /* GRAV_CONSTANT, src/nbody.cu:37 */
+
+typedef struct nb_ctx nb_ctx;
+
+/* Replaces the scalar arguments main() passes to both kernels (src/nbody.cu:481-483). */
+typedef struct nb_params {
+    int   n_max;              /* capacity in bodies (>= every n ever uploaded)                      */
+    float dt;                 /* ConfigData::timestep          include/nbodyConfig.h:8              */
+    float growth;             /* ConfigData::growthRate        include/nbodyConfig.h:13             */
+    int   field_w;            /* ConfigData::fieldWidth        include/nbodyConfig.h:16             */
+    int   field_h;            /* ConfigData::fieldHeight       include/nbodyConfig.h:17             */
+    float grav;               /* 0 -> NB_GRAV_CONSTANT                                              */
+    int   coverage;           /* NB_COVERAGE_*                                                      */
+    int   device;             /* CUDA device ordinal                                                */
+    int   slots_per_body;     /* inline collision-candidate slots per body, 0 -> 8                  */
+    int   overflow_capacity;  /* entries of the shared overflow candidate list, 0 -> max(n_max, 64Ki) */
+    int   event_capacity;     /* 0 = no event log; else records kept between nb_events() calls      */
+    int   rank;               /* this context's shard, 0 <= rank < world                            */
+    int   world;              /* number of shards (GPUs); <= 1 means single GPU                     */
+    int   flags;              /* NB_FLAG_*                                                          */
+} nb_params;
+
+#define NB_FLAG_NO_GRAPH 1    /* launch kernels one by one instead of replaying a CUDA graph        */
+#define NB_FLAG_SCALAR_FORCE 2/* use the scalar-FP32 force kernel instead of the packed f32x2 one   */
+
+typedef struct nb_event {
+    int32_t step;             /* step index (0-based, counted since nb_upload)                      */
+    int32_t i;                /* pre-step index of the body whose row saw the hit                   */
+    int32_t j;                /* pre-step index of the other body                                   */
+    int32_t kind;             /* NB_EV_*                                                            */
+} nb_event;
+
+typedef struct nb_stats {
+    int64_t steps;            /* steps executed since nb_upload                                     */
+    int64_t pairs;            /* ordered pairs evaluated by this context's shard since nb_upload    */
+    int64_t candidates;       /* collision pair-events since nb_upload (this shard)                 */
+    int64_t exact_chunks;     /* 32-body j sub-chunks that took the exact path (this shard)         */
+    int64_t fast_chunks;      /* sub-chunks that took the packed fast path (this shard)             */
+    int32_t n;                /* live bodies now                                                    */
+    int32_t overflow;         /* 1 if the candidate overflow list ever overflowed                   */
+    int32_t events_dropped;   /* 1 if the event log overflowed                                      */
+    int32_t sm_count;         /* multiprocessors of the device                                      */
+    int32_t force_grid;       /* CTAs of the persistent force kernel                                */
+    int32_t force_regs;       /* registers per thread of the force kernel                           */
+} nb_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int  nb_create(nb_ctx **ctx, const nb_params *params);
+void nb_destroy(nb_ctx *ctx);
+const char *nb_last_error(const nb_ctx *ctx);      /* ctx may be NULL: last nb_create error */
+int  nb_version(void);
+
+/* ---- body store --------------------------------------------------------- */
+/*
+ * bodies: the reference's BodiesData block (src/nbody.cu:66-77), 24*n bytes:
+ *   Vec2f Positions[n]; Vec2f Velocities[n]; float Masses[n]; float Radii[n];
+ * nb_upload replaces BodiesData::uploadToDevice (src/nbody.cu:88-96) and
+ * resets the step counter, statistics and event log.  nb_download replaces the
+ * D2H copy + host compaction of src/nbody.cu:486-510: it returns the already
+ * compacted survivors in the same layout (re-laid-out for the current n).
+ * Every rank of a sharded run uploads the same full block.
+ */
+int nb_upload(nb_ctx *ctx, const void *bodies, int n);
+int nb_download(nb_ctx *ctx, void *bodies, int capacity_n, int *n);
+int nb_num_bodies(nb_ctx *ctx, int *n);            /* synchronises */
+
+/* ---- time step ---------------------------------------------------------- */
+/*
+ * n_steps iterations of ComputeForces + MoveBodies + compaction
+ * (src/nbody.cu:481-510).  Asynchronous on the context's stream when world<=1;
+ * errors (candidate overflow, CUDA faults) surface at the next synchronising
+ * call.  nb_step_timed also returns device times measured with CUDA events on
+ * the context's stream: whole region and the force kernel alone (sum).
+ */
+int nb_step(nb_ctx *ctx, int n_steps);
+int nb_step_timed(nb_ctx *ctx, int n_steps, float *ms_total, float *ms_force);
+int nb_sync(nb_ctx *ctx);
+int nb_get_stats(nb_ctx *ctx, nb_stats *out);      /* synchronises */
+
+/*
+ * Derived collision event list: all records logged since the
+ * last nb_events/nb_upload, sorted by (step, i, visit order).  Needs
+ * event_capacity > 0.  Sharded runs return this rank's rows only.
+ */
+int nb_events(nb_ctx *ctx, nb_event *buf, int capacity, int *count);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------ */
+/*
+ * Rank 0 calls nb_comm_unique_id (128 bytes, an ncclUniqueId), the host
+ * distributes it (e.g. torch.distributed / MPI broadcast), then every rank
+ * calls nb_comm_init.  After that nb_step exchanges the shard results with one
+ * ncclAllGather per step over NVLink.
+ */
+#define NB_UNIQUE_ID_BYTES 128
+int nb_comm_unique_id(void *id_out);
+int nb_comm_init(nb_ctx *ctx, const void *id);
+
+/* ---- render (src/nbody.cu:294-348, 350-371) ------------------------------ */
+/* Rasterise the current bodies into a w*h 8-bit image (background 254, body 0). */
+int nb_render(nb_ctx *ctx, uint8_t *image, int w, int h);
+/* Write a binary P5 file exactly as saveImageToDisk does (header "P5\n<w> <h>\n255\n"). */
+int nb_write_pgm(const char *path, const uint8_t *image, int w, int h);
+
+/* ---- driver surface: config, RNG, initial conditions (host only, no GPU) -- */
+/* ConfigData, include/nbodyConfig.h:4-19 (imagePath as a fixed buffer). */
+typedef struct nb_config {
+    int   particleCount;
+    int   totalIterations;
+    int   save_Image_Every_Xth_Iteration;
+    float timestep;
+    float minRandBodyMass;
+    float maxRandBodyMass;
+    float minRadius;
+    float maxRadius;
+    float growthRate;
+    int   imgWidth;
+    int   imgHeight;
+    int   fieldWidth;
+    int   fieldHeight;
+    char  imagePath[1024];
+} nb_config;
+
+/*
+ * parseConfigFile (include/nbodyConfig.h:22-227): same keys, same echo lines
+ * (written to echo_fd, e.g. 1 for stdout; -1 for none), same "Invalid
+ * variable" handling.  Where the reference calls exit(1) this returns
+ * NB_ERR_IO / NB_ERR_INVALID after writing the same message.  Fields whose key
+ * is missing are left untouched (the reference leaves them uninitialised).
+ */
+int nb_config_parse(const char *path, nb_config *cfg, int echo_fd);
+
+/* jbutil::randgen (include/jbutil.h:514-562) */
+typedef struct nb_rng { uint64_t u, v, w; } nb_rng;
+void     nb_rng_seed(nb_rng *g, uint64_t seed);
+uint64_t nb_rng_ival64(nb_rng *g);
+double   nb_rng_fval(nb_rng *g);
+double   nb_rng_fval_range(nb_rng *g, double a, double b);
+
+/* scenarios (NB_SCENARIO_SQUARE is the reference's src/nbody.cu:401-416) */
+#define NB_SCENARIO_SQUARE 0      /* uniform square +-field, v = 0 (reference)                       */
+#define NB_SCENARIO_DISC 1        /* uniform disc of radius `extent`, v = 0                          */
+#define NB_SCENARIO_TWO_GALAXY 2  /* two spinning discs on an encounter course                       */
+typedef struct nb_scenario {
+    int      kind;            /* NB_SCENARIO_*                                                      */
+    int      n;
+    uint64_t seed;            /* 1024 in the reference (src/nbody.cu:403)                           */
+    int      field_w, field_h;
+    float    min_mass, max_mass, min_radius, max_radius;
+    double   extent;          /* disc radius (DISC, TWO_GALAXY); ignored for SQUARE                 */
+} nb_scenario;
+/* Fills a BodiesData block (6*n floats). */
+int nb_generate(const nb_scenario *sc, void *bodies);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H */

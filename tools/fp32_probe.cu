@@ -168,8 +168,10 @@ static float time_ms(F launch, int reps)
     return best;
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    const bool only_pair = argc > 1 && argv[1][0] == 'p';
+    const int only_cps = argc > 2 ? atoi(argv[2]) : 0;
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     int clk_khz = 0;
@@ -182,6 +184,7 @@ int main()
     const double nameplate = (double)sms * 128 * 2 * 1.965e9;
 
     for (int wpsm : {8, 16, 32}) {          // warps per SM
+        if (only_pair) break;
         const int blocks = sms * wpsm / 4, threads = 128, iters = 20000;
         {
             float ms = time_ms([&] { k_ffma<8><<<blocks, threads>>>(out, iters, 1.0001f, 0.5f); }, 5);
@@ -197,7 +200,8 @@ int main()
         }
     }
     for (int cps : {1, 2, 3, 4, 6, 8}) {    // CTAs (4 warps) per SM
-        const int blocks = sms * cps, reps = 400;
+        if (only_cps && cps != only_cps) continue;
+        const int blocks = sms * cps, reps = only_pair ? 50 : 400;
         const double inter = (double)blocks * 128 * IPT * TJ * reps;
         {
             float ms = time_ms([&] { k_pair_scalar<<<blocks, 128>>>(out, reps); }, 5);
