@@ -33,7 +33,7 @@ extern "C" {
 #define NB_ERR_INVALID (-1)           /* bad argument                                   */
 #define NB_ERR_CUDA (-2)              /* CUDA runtime / driver error (see nb_last_error) */
 #define NB_ERR_CAPACITY (-3)          /* n exceeds n_max, or host buffer too small      */
-#define NB_ERR_CANDIDATE_OVERFLOW (-4)/* collision overflow list was too small          */
+#define NB_ERR_CANDIDATE_OVERFLOW (-4)/* collision candidate list was too small         */
 #define NB_ERR_COMM (-5)              /* NCCL error or communicator not initialised     */
 #define NB_ERR_IO (-6)                /* file could not be read / written               */
 #define NB_ERR_EVENT_OVERFLOW (-7)    /* event log was too small (events were dropped)  */
@@ -61,8 +61,8 @@ typedef struct nb_params {
     float grav;               /* 0 -> NB_GRAV_CONSTANT                                              */
     int   coverage;           /* NB_COVERAGE_*                                                      */
     int   device;             /* CUDA device ordinal                                                */
-    int   slots_per_body;     /* inline collision-candidate slots per body, 0 -> 8                  */
-    int   overflow_capacity;  /* entries of the shared overflow candidate list, 0 -> max(n_max, 64Ki) */
+    int   candidate_capacity; /* entries of the per-step collision candidate list (ordered hit
+                                 pairs), 0 -> max(4 * n_max, 64Ki)                                  */
     int   event_capacity;     /* 0 = no event log; else records kept between nb_events() calls      */
     int   rank;               /* this context's shard, 0 <= rank < world                            */
     int   world;              /* number of shards (GPUs); <= 1 means single GPU                     */
@@ -86,11 +86,12 @@ typedef struct nb_stats {
     int64_t exact_chunks;     /* 32-body j sub-chunks that took the exact path (this shard)         */
     int64_t fast_chunks;      /* sub-chunks that took the packed fast path (this shard)             */
     int32_t n;                /* live bodies now                                                    */
-    int32_t overflow;         /* 1 if the candidate overflow list ever overflowed                   */
+    int32_t overflow;         /* 1 if the candidate list ever overflowed                            */
     int32_t events_dropped;   /* 1 if the event log overflowed                                      */
     int32_t sm_count;         /* multiprocessors of the device                                      */
     int32_t force_grid;       /* CTAs of the persistent force kernel                                */
     int32_t force_regs;       /* registers per thread of the force kernel                           */
+    int32_t row_lo, row_hi;   /* this shard's rows [row_lo, row_hi) of the next step                */
 } nb_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -143,6 +144,18 @@ int nb_events(nb_ctx *ctx, nb_event *buf, int capacity, int *count);
 #define NB_UNIQUE_ID_BYTES 128
 int nb_comm_unique_id(void *id_out);
 int nb_comm_init(nb_ctx *ctx, const void *id);
+
+/*
+ * The step plan (coverage descriptor + shard bounds) for n live bodies, computed on the host by
+ * the same code the device runs at the end of every step.  No GPU needed: used by the sharding
+ * tests and by hosts that want to know which rows a rank owns.
+ */
+typedef struct nb_plan {
+    int32_t n, blocks, limit_last, limit_first, n_active, window_len;
+    int32_t row_lo, row_hi, row_act_hi, rows_per_rank, n_iblocks, n_jtiles;
+    int64_t units;
+} nb_plan;
+int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out);
 
 /* ---- render (src/nbody.cu:294-348, 350-371) ------------------------------ */
 /* Rasterise the current bodies into a w*h 8-bit image (background 254, body 0). */

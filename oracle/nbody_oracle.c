@@ -304,6 +304,59 @@ void orc_rows(const float *block, int n, const orc_params *par, const int *rows,
 }
 
 /*
+ * Float64 yardstick for the force sum (NOT the reference's arithmetic): the same visited pairs and
+ * the same float32 collision predicate decide which pairs contribute (src/nbody.cu:210-226), but
+ * direction, distance and the sum itself are evaluated in double.  Used by the tests to show that the
+ * CUDA path's force error is no larger than the reference's own sequential-float32 summation error
+ * (which grows like sqrt(n) * 2^-24).  out is nrows x 2 doubles: dv = dt * G * force per row, i.e. the
+ * velocity change of src/nbody.cu:250-252.
+ */
+void orc_rows_dv_f64(const float *block, int n, const orc_params *par, const int *rows, int nrows, double *out)
+{
+    orc_cov cov;
+    orc_coverage(n, par->coverage, &cov);
+    const float *pos = block, *mass = block + 4 * (size_t)n, *rad = block + 5 * (size_t)n;
+    const int T = ORC_THREADS_PER_BLOCK;
+#ifdef _OPENMP
+    int nt = par->threads > 0 ? par->threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+#endif
+    for (int q = 0; q < nrows; ++q) {
+        const int i = rows[q];
+        double fx = 0.0, fy = 0.0;
+        if (i < cov.n_active) {
+            const int b = i / T, t = i % T;
+            const float xi = pos[2 * i], yi = pos[2 * i + 1], ri = rad[i];
+            int skip = 1;
+            for (int k = 0; k < cov.blocks; ++k) {
+                const int g = (int)(((long long)i + (long long)T * k) % n);
+                const int limit = (k == cov.blocks - 1) ? cov.limit_last : T;
+                const int base = (int)(((long long)T * b + (long long)T * k) % n);
+                int snext = limit > 0 ? t % limit : 0;
+                for (int off = 0; off < limit; ++off) {
+                    const int s = snext;
+                    if (++snext == limit) snext = 0;
+                    if (skip && g == i) { skip = 0; continue; }
+                    int j = base + s;
+                    if (j >= n) j -= n;
+                    const float dxf = pos[2 * j] - xi, dyf = pos[2 * j + 1] - yi;
+                    const float d2f = fmaf(dxf, dxf, dyf * dyf);
+                    const float rs = ri + rad[j];
+                    if (d2f <= rs * rs) continue;                       /* hit: no force from j */
+                    const double dx = (double)pos[2 * j] - (double)xi, dy = (double)pos[2 * j + 1] - (double)yi;
+                    const double d2 = dx * dx + dy * dy;
+                    const double inv = 1.0 / (d2 * sqrt(d2));
+                    fx += dx * (double)mass[j] * inv;
+                    fy += dy * (double)mass[j] * inv;
+                }
+            }
+        }
+        out[2 * q] = (double)par->dt * (fx * (double)ORC_GRAV_CONSTANT);
+        out[2 * q + 1] = (double)par->dt * (fy * (double)ORC_GRAV_CONSTANT);
+    }
+}
+
+/*
  * One full step in place: ComputeForces + MoveBodies for every thread that
  * exists, then the host compaction of src/nbody.cu:488-510 (stable, keeps
  * bodies with mass != 0.f).  `block` holds n bodies in the BodiesData layout

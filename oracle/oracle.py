@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
         L.orc_coverage.argtypes = [C.c_int, C.c_int, C.POINTER(OrcCov)]
         L.orc_rows.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
                                fp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+        L.orc_rows_dv_f64.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
+                                      C.POINTER(C.c_double)]
         L.orc_step.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.c_void_p, C.c_longlong,
                                C.POINTER(C.c_longlong)]
         L.orc_step.restype = C.c_int
@@ -156,6 +158,16 @@ def rows(block: np.ndarray, n: int, par: OrcParams, row_idx):
                    _fptr(out.reshape(-1)), hits.ctypes.data_as(C.POINTER(C.c_int)),
                    visited.ctypes.data_as(C.POINTER(C.c_longlong)))
     return out, hits, visited
+
+
+def rows_dv_f64(block: np.ndarray, n: int, par: OrcParams, row_idx) -> np.ndarray:
+    """Float64 yardstick: dv = dt * G * force of selected rows with the sum evaluated in double
+    (same visited pairs, same float32 collision predicate).  Returns [nrows, 2] float64."""
+    idx = np.ascontiguousarray(row_idx, dtype=np.int32)
+    out = np.zeros((len(idx), 2), dtype=np.float64)
+    lib().orc_rows_dv_f64(_fptr(block), n, C.byref(par), idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx),
+                          out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
 
 
 def fnv(a: np.ndarray, h: int = 0) -> int:

@@ -1,0 +1,557 @@
+// nbody_api.cu -- the C ABI of include/nbody_b200.h over the kernels in nbody_kernels.cu.
+//
+// Replaces the body of the reference's main loop (src/nbody.cu:460-545): where the reference
+// re-allocates, uploads, launches, downloads and compacts on the host every step, a context here
+// owns all device memory once, keeps n on the device and replays one CUDA graph per step.
+// There is no CPU fallback: without a usable sm_100 device nb_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library itself is bound at run time (see nccl_api below)
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "nbody_device.cuh"
+
+using namespace nb;
+
+struct nb_ctx {
+    nb_params par;
+    DevState st;
+    StepParams sp;
+    int device;
+    int sm_count;
+    int force_regs;
+    bool packed;
+    cudaStream_t stream;
+    cudaGraphExec_t graph;
+    bool graph_ready;
+    cudaEvent_t ev0, ev1;
+    std::vector<cudaEvent_t> fev;     // per-step force-kernel brackets of nb_step_timed
+    ncclComm_t comm;
+    bool comm_ready;
+    void *dev_block;                   // staging for upload/download: the BodiesData block, 24 * cap bytes
+    unsigned char *dev_img;
+    size_t dev_img_bytes;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+// NCCL is bound lazily with dlopen so that (a) single-GPU users need no NCCL at all and (b) inside a
+// process that already loaded an NCCL (e.g. torch's bundled one) we share that copy instead of
+// bringing a second one.
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi *nccl_api()
+{
+    static NcclApi api = {};
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString) api.lib = h;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+
+static void set_err(nb_ctx *c, const char *fmt, ...)
+{
+    char *dst = c ? c->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+}
+
+#define NB_CUDA(c, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            set_err(c, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return NB_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define NB_NCCL(c, call)                                                                              \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess) {                                                                      \
+            set_err(c, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+            return NB_ERR_COMM;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+extern "C" {
+
+int nb_version(void) { return NB_VERSION; }
+
+const char *nb_last_error(const nb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+static void free_all(nb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm_ready) nccl_api()->CommDestroy(c->comm);
+    if (c->graph_ready) cudaGraphExecDestroy(c->graph);
+    for (cudaEvent_t e : c->fev) cudaEventDestroy(e);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    void *ptrs[] = {c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.head, c->st.cand,
+                    c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete c;
+}
+
+int nb_create(nb_ctx **out, const nb_params *params)
+{
+    if (!out || !params) {
+        set_err(nullptr, "nb_create: null argument");
+        return NB_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (params->n_max <= 0 || params->n_max > (1 << 26) || params->field_w <= 0 || params->field_h <= 0 ||
+        (params->coverage != NB_COVERAGE_REFERENCE && params->coverage != NB_COVERAGE_FULL) ||
+        (params->world > 1 && (params->rank < 0 || params->rank >= params->world))) {
+        set_err(nullptr, "nb_create: invalid parameters");
+        return NB_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_err(nullptr, "nb_create: no CUDA device (this library has no CPU fallback)");
+        return NB_ERR_CUDA;
+    }
+    if (params->device < 0 || params->device >= ndev) {
+        set_err(nullptr, "nb_create: device %d out of range (%d devices)", params->device, ndev);
+        return NB_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    NB_CUDA(nullptr, cudaGetDeviceProperties(&prop, params->device));
+    if (prop.major != 10) {
+        set_err(nullptr, "nb_create: device %d is sm_%d%d; this library is built for sm_100a only", params->device,
+                prop.major, prop.minor);
+        return NB_ERR_CUDA;
+    }
+    nb_ctx *c = new (std::nothrow) nb_ctx();
+    if (!c) return NB_ERR_INVALID;
+    c->par = *params;
+    c->device = params->device;
+    c->sm_count = prop.multiProcessorCount;
+    c->err[0] = 0;
+    NB_CUDA(nullptr, cudaSetDevice(c->device));
+
+    const int world = params->world > 1 ? params->world : 1;
+    DevState &st = c->st;
+    st.cap = params->n_max;
+    const int iblocks_total = (st.cap + kIBlock - 1) / kIBlock;
+    st.shard_cap = (iblocks_total + world - 1) / world * kIBlock;
+    st.cand_cap = params->candidate_capacity > 0 ? params->candidate_capacity
+                                                 : (int)std::min<long long>(std::max<long long>(4LL * st.cap, 65536), 1LL << 30);
+    st.ev_cap = params->event_capacity > 0 ? params->event_capacity : 0;
+
+    c->packed = !(params->flags & NB_FLAG_SCALAR_FORCE);
+    const int occ = force_occupancy(c->packed, &c->force_regs);
+    if (occ <= 0) {
+        set_err(nullptr, "nb_create: force kernel does not fit on an SM");
+        free_all(c);
+        return NB_ERR_CUDA;
+    }
+    StepParams &sp = c->sp;
+    sp.dt = params->dt;
+    sp.growth = params->growth;
+    sp.grav = params->grav != 0.f ? params->grav : NB_GRAV_CONSTANT;
+    sp.field_w = params->field_w;
+    sp.field_h = params->field_h;
+    sp.coverage = params->coverage;
+    sp.rank = world > 1 ? params->rank : 0;
+    sp.world = world;
+    sp.force_grid = c->sm_count * occ;
+    sp.count_stats = 1;
+
+    const size_t tiles = (size_t)(st.cap + kTJ - 1) / kTJ + 1;
+    const size_t ctiles = (size_t)(st.cap + kCompactTile - 1) / kCompactTile;
+#define NB_ALLOC(ptr, bytes)                                                                    \
+    do {                                                                                        \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                  \
+        if (e_ != cudaSuccess) {                                                                \
+            set_err(nullptr, "cudaMalloc(%s, %zu) failed: %s", #ptr, (size_t)(bytes), cudaGetErrorString(e_)); \
+            free_all(c);                                                                        \
+            return NB_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+    NB_ALLOC(st.pm, sizeof(float4) * (size_t)st.cap);
+    NB_ALLOC(st.vel, sizeof(float2) * (size_t)st.cap);
+    NB_ALLOC(st.jt, (size_t)kTileBytes * tiles);
+    NB_ALLOC(st.post, (size_t)world * st.shard_cap * 24);
+    NB_ALLOC(st.fpart, sizeof(float2) * kIBlock * fpart_slabs(sp.force_grid, st.shard_cap));
+    NB_ALLOC(st.head, sizeof(int) * (size_t)st.cap);
+    NB_ALLOC(st.cand, sizeof(int2) * (size_t)st.cand_cap);
+    if (st.ev_cap > 0) NB_ALLOC(st.ev, sizeof(EventRec) * (size_t)st.ev_cap);
+    NB_ALLOC(st.tile_count, sizeof(int) * ctiles);
+    NB_ALLOC(st.desc, sizeof(StepDesc));
+    NB_ALLOC(st.res, sizeof(StepResult));
+    NB_ALLOC(st.ctr, sizeof(Counters));
+    NB_ALLOC(c->dev_block, (size_t)24 * st.cap);
+#undef NB_ALLOC
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(st.res, 0, sizeof(StepResult), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(st.head, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
+    if (e == cudaSuccess) e = launch_plan(st, sp, 0, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        set_err(nullptr, "nb_create: %s", cudaGetErrorString(e));
+        free_all(c);
+        return NB_ERR_CUDA;
+    }
+    *out = c;
+    return NB_OK;
+}
+
+void nb_destroy(nb_ctx *ctx) { free_all(ctx); }
+
+int nb_upload(nb_ctx *c, const void *bodies, int n)
+{
+    if (!c || (!bodies && n > 0) || n < 0) return NB_ERR_INVALID;
+    if (n > c->st.cap) {
+        set_err(c, "nb_upload: n = %d exceeds n_max = %d", n, c->st.cap);
+        return NB_ERR_CAPACITY;
+    }
+    NB_CUDA(c, cudaSetDevice(c->device));
+    if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
+    NB_CUDA(c, launch_ingest(c->st, (const float *)c->dev_block, n, c->stream));
+    NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
+    // the caller may reuse `bodies` as soon as we return
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NB_OK;
+}
+
+static int check_flags(nb_ctx *c, const Counters &ctr)
+{
+    if (ctr.overflow_flag) {
+        set_err(c, "collision candidate list overflowed (capacity %d): results after that step are invalid", c->st.cand_cap);
+        return NB_ERR_CANDIDATE_OVERFLOW;
+    }
+    return NB_OK;
+}
+
+static int fetch_state(nb_ctx *c, StepDesc *d, Counters *ctr)
+{
+    NB_CUDA(c, cudaSetDevice(c->device));
+    if (d) NB_CUDA(c, cudaMemcpyAsync(d, c->st.desc, sizeof(StepDesc), cudaMemcpyDeviceToHost, c->stream));
+    if (ctr) NB_CUDA(c, cudaMemcpyAsync(ctr, c->st.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NB_OK;
+}
+
+int nb_sync(nb_ctx *c)
+{
+    if (!c) return NB_ERR_INVALID;
+    Counters ctr;
+    int rc = fetch_state(c, nullptr, &ctr);
+    if (rc != NB_OK) return rc;
+    return check_flags(c, ctr);
+}
+
+int nb_num_bodies(nb_ctx *c, int *n)
+{
+    if (!c || !n) return NB_ERR_INVALID;
+    StepDesc d;
+    Counters ctr;
+    int rc = fetch_state(c, &d, &ctr);
+    if (rc != NB_OK) return rc;
+    *n = d.n;
+    return check_flags(c, ctr);
+}
+
+int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
+{
+    if (!c || !n_out) return NB_ERR_INVALID;
+    StepDesc d;
+    Counters ctr;
+    int rc = fetch_state(c, &d, &ctr);
+    if (rc != NB_OK) return rc;
+    *n_out = d.n;
+    if (d.n > capacity_n || (!bodies && d.n > 0)) {
+        set_err(c, "nb_download: host buffer holds %d bodies, %d are live", capacity_n, d.n);
+        return NB_ERR_CAPACITY;
+    }
+    if (d.n > 0) {
+        NB_CUDA(c, launch_export(c->st, (float *)c->dev_block, d.n, c->stream));
+        NB_CUDA(c, cudaMemcpyAsync(bodies, c->dev_block, (size_t)24 * d.n, cudaMemcpyDeviceToHost, c->stream));
+        NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return check_flags(c, ctr);
+}
+
+// one step's launches on the context's stream; f0/f1 (optional) bracket the force kernel
+static int enqueue_step(nb_ctx *c, cudaEvent_t f0, cudaEvent_t f1)
+{
+    if (f0) NB_CUDA(c, cudaEventRecord(f0, c->stream));
+    NB_CUDA(c, launch_force(c->st, c->sp, c->packed, c->stream));
+    if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
+    NB_CUDA(c, launch_finish(c->st, c->sp, c->stream));
+    if (c->sp.world > 1) {
+        const size_t chunk = (size_t)c->st.shard_cap * 24;
+        NB_NCCL(c, nccl_api()->AllGather(c->st.post + (size_t)c->sp.rank * chunk, c->st.post, chunk, ncclChar, c->comm, c->stream));
+    }
+    NB_CUDA(c, launch_compact(c->st, c->sp, c->stream));
+    return NB_OK;
+}
+
+static int ensure_graph(nb_ctx *c)
+{
+    if (c->graph_ready) return NB_OK;
+    cudaGraph_t g = nullptr;
+    NB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(c, nullptr, nullptr);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc != NB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    NB_CUDA(c, e);
+    e = cudaGraphInstantiate(&c->graph, g, 0);
+    cudaGraphDestroy(g);
+    NB_CUDA(c, e);
+    c->graph_ready = true;
+    return NB_OK;
+}
+
+static int step_precheck(nb_ctx *c, int n_steps)
+{
+    if (!c || n_steps < 0) return NB_ERR_INVALID;
+    if (c->sp.world > 1 && !c->comm_ready) {
+        set_err(c, "nb_step: world = %d but nb_comm_init has not been called", c->sp.world);
+        return NB_ERR_COMM;
+    }
+    NB_CUDA(c, cudaSetDevice(c->device));
+    return NB_OK;
+}
+
+int nb_step(nb_ctx *c, int n_steps)
+{
+    int rc = step_precheck(c, n_steps);
+    if (rc != NB_OK) return rc;
+    if (c->par.flags & NB_FLAG_NO_GRAPH) {
+        for (int s = 0; s < n_steps; ++s)
+            if ((rc = enqueue_step(c, nullptr, nullptr)) != NB_OK) return rc;
+    } else {
+        if ((rc = ensure_graph(c)) != NB_OK) return rc;
+        for (int s = 0; s < n_steps; ++s) NB_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
+    }
+    if (c->sp.world > 1) NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NB_OK;
+}
+
+int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
+{
+    int rc = step_precheck(c, n_steps);
+    if (rc != NB_OK) return rc;
+    if (ms_total) *ms_total = 0.f;
+    if (ms_force) *ms_force = 0.f;
+    if (!ms_force) {            // whole region only: keep the graph path
+        NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        if (c->par.flags & NB_FLAG_NO_GRAPH) {
+            for (int s = 0; s < n_steps; ++s)
+                if ((rc = enqueue_step(c, nullptr, nullptr)) != NB_OK) return rc;
+        } else {
+            if ((rc = ensure_graph(c)) != NB_OK) return rc;
+            for (int s = 0; s < n_steps; ++s) NB_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
+        }
+        NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        NB_CUDA(c, cudaEventSynchronize(c->ev1));
+        if (ms_total) NB_CUDA(c, cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
+        return NB_OK;
+    }
+    while ((int)c->fev.size() < 2 * n_steps) {
+        cudaEvent_t e;
+        NB_CUDA(c, cudaEventCreate(&e));
+        c->fev.push_back(e);
+    }
+    NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int s = 0; s < n_steps; ++s)
+        if ((rc = enqueue_step(c, c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
+    NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    NB_CUDA(c, cudaEventSynchronize(c->ev1));
+    if (ms_total) NB_CUDA(c, cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
+    float sum = 0.f;
+    for (int s = 0; s < n_steps; ++s) {
+        float ms = 0.f;
+        NB_CUDA(c, cudaEventElapsedTime(&ms, c->fev[2 * s], c->fev[2 * s + 1]));
+        sum += ms;
+    }
+    *ms_force = sum;
+    return NB_OK;
+}
+
+int nb_get_stats(nb_ctx *c, nb_stats *out)
+{
+    if (!c || !out) return NB_ERR_INVALID;
+    StepDesc d;
+    Counters ctr;
+    int rc = fetch_state(c, &d, &ctr);
+    if (rc != NB_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    out->steps = (int64_t)ctr.steps;
+    out->pairs = (int64_t)ctr.pairs;
+    out->candidates = (int64_t)ctr.candidates;
+    out->exact_chunks = (int64_t)ctr.exact_chunks;
+    out->fast_chunks = (int64_t)ctr.fast_chunks;
+    out->n = d.n;
+    out->overflow = ctr.overflow_flag;
+    out->events_dropped = ctr.ev_dropped;
+    out->sm_count = c->sm_count;
+    out->force_grid = c->sp.force_grid;
+    out->force_regs = c->force_regs;
+    out->row_lo = d.row_lo;
+    out->row_hi = d.row_hi;
+    return NB_OK;
+}
+
+int nb_events(nb_ctx *c, nb_event *buf, int capacity, int *count)
+{
+    if (!c || !count || capacity < 0 || (!buf && capacity > 0)) return NB_ERR_INVALID;
+    *count = 0;
+    if (c->st.ev_cap <= 0) {
+        set_err(c, "nb_events: the context was created with event_capacity = 0");
+        return NB_ERR_INVALID;
+    }
+    Counters ctr;
+    int rc = fetch_state(c, nullptr, &ctr);
+    if (rc != NB_OK) return rc;
+    const unsigned have = std::min<unsigned>(ctr.ev_count, (unsigned)c->st.ev_cap);
+    std::vector<EventRec> rec(have);
+    if (have > 0)
+        NB_CUDA(c, cudaMemcpy(rec.data(), c->st.ev, sizeof(EventRec) * have, cudaMemcpyDeviceToHost));
+    // reset the log
+    unsigned zero = 0;
+    NB_CUDA(c, cudaMemcpy(&c->st.ctr->ev_count, &zero, sizeof(unsigned), cudaMemcpyHostToDevice));
+    std::sort(rec.begin(), rec.end(), [](const EventRec &a, const EventRec &b) {
+        if (a.step != b.step) return a.step < b.step;
+        if (a.i != b.i) return a.i < b.i;
+        return (a.key_kind >> 1) < (b.key_kind >> 1);
+    });
+    *count = (int)have;
+    if ((int)have > capacity) {
+        set_err(c, "nb_events: %u records, buffer holds %d", have, capacity);
+        return NB_ERR_CAPACITY;
+    }
+    for (unsigned k = 0; k < have; ++k) {
+        buf[k].step = rec[k].step;
+        buf[k].i = rec[k].i;
+        buf[k].j = rec[k].j;
+        buf[k].kind = (int32_t)(rec[k].key_kind & 1u);
+    }
+    if (ctr.ev_dropped) {
+        set_err(c, "nb_events: the event log overflowed (capacity %d); records were dropped", c->st.ev_cap);
+        return NB_ERR_EVENT_OVERFLOW;
+    }
+    return NB_OK;
+}
+
+int nb_comm_unique_id(void *id_out)
+{
+    if (!id_out) return NB_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) == NB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (!nccl_api()) {
+        set_err(nullptr, "libnccl.so.2 could not be loaded");
+        return NB_ERR_COMM;
+    }
+    if (nccl_api()->GetUniqueId(&id) != ncclSuccess) {
+        set_err(nullptr, "ncclGetUniqueId failed");
+        return NB_ERR_COMM;
+    }
+    memcpy(id_out, &id, sizeof(id));
+    return NB_OK;
+}
+
+int nb_comm_init(nb_ctx *c, const void *id_bytes)
+{
+    if (!c || !id_bytes) return NB_ERR_INVALID;
+    if (c->sp.world <= 1) return NB_OK;
+    if (c->comm_ready) return NB_OK;
+    if (!nccl_api()) {
+        set_err(c, "libnccl.so.2 could not be loaded");
+        return NB_ERR_COMM;
+    }
+    NB_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    NB_NCCL(c, nccl_api()->CommInitRank(&c->comm, c->sp.world, id, c->sp.rank));
+    c->comm_ready = true;
+    return NB_OK;
+}
+
+int nb_render(nb_ctx *c, uint8_t *image, int w, int h)
+{
+    if (!c || !image || w <= 0 || h <= 0) return NB_ERR_INVALID;
+    StepDesc d;
+    int rc = fetch_state(c, &d, nullptr);
+    if (rc != NB_OK) return rc;
+    const size_t bytes = (size_t)w * h;
+    if (bytes > c->dev_img_bytes) {
+        if (c->dev_img) cudaFree(c->dev_img);
+        c->dev_img = nullptr;
+        c->dev_img_bytes = 0;
+        NB_CUDA(c, cudaMalloc((void **)&c->dev_img, bytes));
+        c->dev_img_bytes = bytes;
+    }
+    NB_CUDA(c, cudaMemsetAsync(c->dev_img, 254, bytes, c->stream));      // src/nbody.cu:534
+    NB_CUDA(c, launch_render(c->st, d.n, c->dev_img, w, h, c->sp.field_w, c->sp.field_h, c->stream));
+    NB_CUDA(c, cudaMemcpyAsync(image, c->dev_img, bytes, cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NB_OK;
+}
+
+int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
+{
+    if (!params || !out || n < 0) return NB_ERR_INVALID;
+    StepParams sp = {};
+    sp.coverage = params->coverage;
+    sp.world = params->world > 1 ? params->world : 1;
+    sp.rank = params->world > 1 ? params->rank : 0;
+    sp.force_grid = force_grid;
+    StepDesc d;
+    plan_host(&d, &sp, n);
+    out->n = d.n;
+    out->blocks = d.blocks;
+    out->limit_last = d.limit_last;
+    out->limit_first = d.limit_first;
+    out->n_active = d.n_active;
+    out->window_len = d.window_len;
+    out->row_lo = d.row_lo;
+    out->row_hi = d.row_hi;
+    out->row_act_hi = d.row_act_hi;
+    out->rows_per_rank = d.rows_per_rank;
+    out->n_iblocks = d.n_iblocks;
+    out->n_jtiles = d.n_jtiles;
+    out->units = d.units;
+    return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// nbody_device.cuh -- device-side data layout shared by the kernels and the C ABI.
+//
+// HBM layout (all arrays owned by the context, allocated once for n_max bodies):
+//   pm   [cap]          float4 {x, y, m, r}   current compacted bodies (the i side, 16 B coalesced)
+//   vel  [cap]          float2 {vx, vy}
+//   jt   [tiles][4][256] float                 the same bodies as planar 4 KB j-tiles {x[256] y[256] m[256] r[256]}:
+//                                              one 1-D TMA bulk copy per tile; the last tile is padded with
+//                                              benign bodies (far away, m = 0, r = 0)
+//   post [world][shard_cap*24 B]               uncompacted post-step rows, one chunk per rank:
+//                                              float4 pm[shard_cap] then float2 vel[shard_cap]  (allgather payload)
+//   fpart[G + iblocks][512] float2             partial force sums, one slab per (force CTA, i-block) segment,
+//                                              summed in CTA order by the finish kernel (deterministic)
+//   head [cap] int, cand[cand_cap] int2{j,next} collision candidates: one global list filled through
+//                                              warp-aggregated atomics, threaded into per-row chains
+//   tile_count[cap/1024] int                   survivors per compaction tile
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nbody_b200.h"
+
+namespace nb {
+
+constexpr int kGroup = 128;                  // rows per visit-order group == reference THREADS_PER_BLOCK (src/nbody.cu:36)
+constexpr int kIPT = 4;                      // rows per lane
+constexpr int kWarps = 4;                    // warps per force CTA; one warp == one 128-row group
+constexpr int kForceThreads = kWarps * 32;
+constexpr int kIBlock = kWarps * kGroup;     // 512 rows per i-block
+constexpr int kTJ = 256;                     // j bodies per shared-memory tile
+constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
+constexpr int kTileBytes = kTileFloats * 4;
+constexpr int kSC = 32;                      // j bodies per sub-chunk (granularity of the collision pre-test)
+constexpr int kStages = 4;                   // TMA ring depth
+constexpr int kCompactThreads = 256;
+constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
+constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
+constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
+
+struct StepDesc {                 // rewritten on the device at the end of every step (plan)
+    int n;                        // live bodies
+    int blocks;                   // B: j tiles of the reference's visit order        (src/nbody.cu:473)
+    int limit_last;               // slots of tile B-1                                (src/nbody.cu:194)
+    int limit_first;              // slots of tile 0 (128 unless B == 1)
+    int n_active;                 // bodies that own a thread                         (src/nbody.cu:142-143)
+    int window_len;               // L = 128 (B-1) + limit_last: length of every group's cyclic j window
+    int excl_len;                 // n - L: bodies cyclically preceding a group's start that it never visits
+    int row_lo, row_hi;           // this rank's rows [row_lo, row_hi) of [0, n)
+    int row_act_hi;               // min(row_hi, n_active), >= row_lo
+    int rows_per_rank;            // rows per rank this step (multiple of 512)
+    int n_iblocks;                // 512-row i-blocks holding this rank's active rows
+    int n_jtiles;                 // T = ceil(n / 256)
+    int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
+    long long units;              // U = n_iblocks * T  (i-block x j-tile work units of this rank)
+    float rmax;                   // max radius over live bodies
+    unsigned step;                // steps since upload
+};
+
+struct StepResult {               // accumulated by the scatter kernel, consumed by plan
+    unsigned rmax_bits;
+    unsigned ticket;
+};
+
+struct Counters {
+    unsigned long long pairs;
+    unsigned long long candidates;
+    unsigned long long exact_chunks;
+    unsigned long long fast_chunks;
+    unsigned long long steps;
+    unsigned cand_count;          // entries pushed to the candidate list this step
+    int overflow_flag;            // sticky
+    unsigned ev_count;            // event records logged since the last nb_events
+    int ev_dropped;               // sticky
+};
+
+struct EventRec {                 // device-side event record (sorted and unpacked on the host)
+    int step, i, j;
+    unsigned key_kind;            // visit-order key << 1 | kind
+};
+
+struct StepParams {
+    float dt, growth, grav;
+    int field_w, field_h;
+    int coverage;
+    int rank, world;
+    int force_grid;
+    int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
+};
+
+struct DevState {
+    float4 *pm;
+    float2 *vel;
+    float *jt;
+    unsigned char *post;          // world chunks of shard_cap * 24 B
+    float2 *fpart;
+    int *head;
+    int2 *cand;
+    EventRec *ev;
+    int *tile_count;
+    StepDesc *desc;
+    StepResult *res;
+    Counters *ctr;
+    int cap;                      // n_max
+    int shard_cap;                // rows per rank chunk in `post` (multiple of 512)
+    int cand_cap;
+    int ev_cap;
+};
+
+__host__ __device__ inline float4 *post_pm(const DevState &st, int rank)
+{
+    return reinterpret_cast<float4 *>(st.post + (size_t)rank * st.shard_cap * 24);
+}
+__host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
+{
+    return reinterpret_cast<float2 *>(st.post + (size_t)rank * st.shard_cap * 24 + (size_t)st.shard_cap * 16);
+}
+
+// kernels (nbody_kernels.cu)
+cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
+cudaError_t launch_force(const DevState &st, const StepParams &p, bool packed, cudaStream_t s);
+cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
+cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s);
+cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s);
+cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s);
+cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
+                          cudaStream_t s);
+int force_occupancy(bool packed, int *regs);   // resident CTAs per SM of the force kernel
+size_t fpart_slabs(int force_grid, int shard_cap);   // slabs of 512 float2 needed
+void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
+
+}  // namespace nb

@@ -1,0 +1,797 @@
+// nbody_kernels.cu -- hand-written sm_100a kernels of the ppa-nbody-collisions time step.
+//
+// One step = force (ComputeForces' O(n^2) pair loop, src/nbody.cu:182-242)
+//          -> finish (collision bookkeeping :215-226,245-246, velocity + walls :250-264, MoveBodies :277-292)
+//          -> [allgather of the post-step rows when sharded]
+//          -> count + scatter (the host compaction of :488-510 as a stable device compaction) + plan of the next step.
+//
+// Compiled with -fmad=false: every fused multiply-add below is written explicitly and sits exactly where
+// the reference's PTX has one (SURVEY.md 8a "arithmetic contract"); the force sum itself uses rsqrt and a
+// different summation order and is therefore tolerance-checked, not bit-exact.
+#include "nbody_device.cuh"
+
+namespace nb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned addr = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: the coverage descriptor of the next step (src/nbody.cu:473, :194, :142-143) + sharding
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int n, float rmax, unsigned step)
+{
+    const int T = kGroup;
+    d.n = n;
+    if (p.coverage == NB_COVERAGE_REFERENCE) {
+        d.blocks = n < T ? 1 : n / T;                         // src/nbody.cu:473 (floor)
+        d.limit_last = n % (T + 1);                           // src/nbody.cu:194
+        const int threads = d.blocks * T;
+        d.n_active = n < threads ? n : threads;               // src/nbody.cu:142-143
+    } else {
+        d.blocks = (n + T - 1) / T;
+        d.limit_last = d.blocks > 0 ? n - T * (d.blocks - 1) : 0;
+        d.n_active = n;
+    }
+    d.limit_first = d.blocks <= 1 ? d.limit_last : T;
+    d.window_len = d.blocks > 0 ? T * (d.blocks - 1) + d.limit_last : 0;
+    d.excl_len = n - d.window_len;
+    const int world = p.world > 1 ? p.world : 1;
+    const int rank = p.world > 1 ? p.rank : 0;
+    const int iblocks_total = (n + kIBlock - 1) / kIBlock;
+    const int per_rank = (iblocks_total + world - 1) / world;
+    d.rows_per_rank = per_rank * kIBlock;
+    long long lo = (long long)rank * d.rows_per_rank;
+    d.row_lo = lo < n ? (int)lo : n;
+    long long hi = lo + d.rows_per_rank;
+    d.row_hi = hi < n ? (int)hi : n;
+    if (d.row_hi < d.row_lo) d.row_hi = d.row_lo;
+    d.row_act_hi = d.row_hi < d.n_active ? d.row_hi : d.n_active;
+    if (d.row_act_hi < d.row_lo) d.row_act_hi = d.row_lo;
+    d.n_iblocks = (d.row_act_hi - d.row_lo + kIBlock - 1) / kIBlock;
+    d.n_jtiles = (n + kTJ - 1) / kTJ;
+    d.force_exact = n < 2 * T ? 1 : 0;
+    d.units = (long long)d.n_iblocks * d.n_jtiles;
+    d.rmax = rmax;
+    d.step = step;
+}
+
+__global__ void plan_kernel(DevState st, StepParams p, int n)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StepDesc d;
+    plan_fill(d, p, n, __uint_as_float(st.res->rmax_bits), 0u);
+    *st.desc = d;
+    st.res->rmax_bits = 0u;
+    st.res->ticket = 0u;
+    Counters c = {};
+    *st.ctr = c;
+}
+
+// owner(u): the force CTA whose unit range [c U / G, (c+1) U / G) holds unit u
+__device__ __forceinline__ int unit_owner(long long u, long long U, int G)
+{
+    return (int)(((u + 1) * (long long)G - 1) / U);
+}
+
+// visit-order key of candidate j for row i: tile k ascending, then off with s = (t + off) % limit
+// (src/nbody.cu:182-207)
+__device__ __forceinline__ int visit_key(const StepDesc &d, int i, int j)
+{
+    const int gbase = i & ~(kGroup - 1), t = i & (kGroup - 1);
+    int q = j - gbase;
+    if (q < 0) q += d.n;
+    const int k = q >> 7, s = q & (kGroup - 1);
+    const int limit = (k == d.blocks - 1) ? d.limit_last : kGroup;
+    int off = s - (t % limit);
+    if (off < 0) off += limit;
+    return k * kGroup + off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// force kernel
+// ------------------------------------------------------------------------------------------------
+// (hi, lo) += x with the rounding error of hi + x captured in lo (Knuth TwoSum; needs -fmad=false and
+// no fast-math, which is how this file is compiled)
+__device__ __forceinline__ void two_sum(float &hi, float &lo, const float x)
+{
+    const float s = hi + x;
+    const float bb = s - hi;
+    const float err = (hi - (s - bb)) + (x - bb);
+    hi = s;
+    lo += err;
+}
+
+struct Window {            // the j ranges a group never visits: [a0,b0) u [a1,b1)
+    int a0, b0, a1, b1;
+};
+
+template <bool PACKED>
+__device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const float2 ms, const float2 nxi,
+                                      const float2 nyi, const float thr, float2 &fx, float2 &fy, bool &cand)
+{
+    if (PACKED) {
+        const float2 dx = __fadd2_rn(xs, nxi);
+        const float2 dy = __fadd2_rn(ys, nyi);
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        cand |= (d2.x <= thr);
+        cand |= (d2.y <= thr);
+        const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+        const float2 s = __fmul2_rn(__fmul2_rn(inv, inv), __fmul2_rn(inv, ms));
+        fx = __ffma2_rn(dx, s, fx);
+        fy = __ffma2_rn(dy, s, fy);
+    } else {
+        const float dx0 = xs.x + nxi.x, dy0 = ys.x + nyi.x;
+        const float dx1 = xs.y + nxi.y, dy1 = ys.y + nyi.y;
+        const float d20 = fmaf(dx0, dx0, dy0 * dy0), d21 = fmaf(dx1, dx1, dy1 * dy1);
+        cand |= (d20 <= thr);
+        cand |= (d21 <= thr);
+        const float i0 = rsqrt_approx(d20), i1 = rsqrt_approx(d21);
+        const float s0 = (i0 * i0) * (i0 * ms.x), s1 = (i1 * i1) * (i1 * ms.y);
+        fx.x = fmaf(dx0, s0, fx.x);
+        fy.x = fmaf(dy0, s0, fy.x);
+        fx.y = fmaf(dx1, s1, fx.y);
+        fy.y = fmaf(dy1, s1, fy.y);
+    }
+}
+
+// Exact evaluation of one body j for one row: the reference predicate (src/nbody.cu:126-134), its
+// bookkeeping split (hit pairs are excluded from the force sum, :215-226) and candidate emission.
+__device__ __forceinline__ void exact_one(const DevState &st, const float *tile, const int jj, const int j,
+                                          const float xi, const float yi, const float ri, const bool active,
+                                          const int row, const int excl, const Window &w, float &fxl, float &fyl,
+                                          const int lane)
+{
+    const float xj = tile[jj], yj = tile[kTJ + jj], mj = tile[2 * kTJ + jj], rj = tile[3 * kTJ + jj];
+    const float dx = xj - xi, dy = yj - yi;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float rs = ri + rj;
+    const float rs2 = rs * rs;
+    const bool hit = d2 <= rs2;
+    const bool in_excl = ((j >= w.a0) & (j < w.b0)) | ((j >= w.a1) & (j < w.b1));
+    const bool valid = active & (j != excl) & !in_excl;
+    const float inv = rsqrt_approx(d2);
+    const float s = (inv * inv) * (inv * mj);
+    if (valid && !hit) {
+        fxl = fmaf(dx, s, fxl);
+        fyl = fmaf(dy, s, fyl);
+    }
+    const bool push = valid && hit;
+    const unsigned mask = __ballot_sync(0xffffffffu, push);
+    if (mask) {                                   // warp-aggregated reservation in the global candidate list
+        const int leader = __ffs(mask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&st.ctr->cand_count, (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (push) {
+            const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
+            if (idx < (unsigned)st.cand_cap) {
+                const int prev = atomicExch(&st.head[row], (int)idx);
+                st.cand[idx] = make_int2(j, prev);
+            } else {
+                st.ctr->overflow_flag = 1;
+            }
+        }
+    }
+}
+
+template <bool PACKED, int MINB>
+__global__ void __launch_bounds__(kForceThreads, MINB) force_kernel(const DevState st, const StepParams p)
+{
+    __shared__ __align__(128) float tiles[kStages][kTileFloats];
+    __shared__ __align__(8) unsigned long long full_bar[kStages];
+    __shared__ __align__(8) unsigned long long empty_bar[kStages];
+    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per tile with a
+    // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one
+    // 128-term float sum instead of growing like sqrt(n) as a single running float sum does
+    __shared__ float4 acc_s[kIPT][kForceThreads];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long U = st.desc->units;
+    const int c = blockIdx.x;
+    const int G = (long long)gridDim.x < U ? (int)gridDim.x : (int)U;   // CTAs that own at least one unit
+    if (c >= G) return;
+    const long long u0 = (long long)c * U / G, u1 = (long long)(c + 1) * U / G;
+    if (u0 >= u1) return;
+    const int nt = (int)(u1 - u0);
+    const int T = st.desc->n_jtiles;
+    const int n = st.desc->n;
+    const int row_lo = st.desc->row_lo, row_act_hi = st.desc->row_act_hi;
+    const int excl_len = st.desc->excl_len, limit_first = st.desc->limit_first;
+    const bool fexact = st.desc->force_exact != 0;
+    const float rmax = st.desc->rmax;
+
+    int ib = (int)(u0 / T);
+    int tile = (int)(u0 - (long long)ib * T);
+    int ptile = tile;                             // next tile the producer issues
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int pre = nt < kStages - 1 ? nt : kStages - 1;
+        for (int k = 0; k < pre; ++k) {
+            mbar_expect_tx(&full_bar[k], kTileBytes);
+            bulk_g2s(tiles[k], st.jt + (size_t)ptile * kTileFloats, kTileBytes, &full_bar[k]);
+            ptile = ptile + 1 == T ? 0 : ptile + 1;
+        }
+    }
+
+    float2 nxi[kIPT], nyi[kIPT], fx[kIPT], fy[kIPT];
+    float thr[kIPT], ri[kIPT];
+    Window w = {0, 0, 0, 0};
+    int gbase = 0;
+    bool warp_active = false;
+    unsigned n_fast = 0, n_exact = 0;
+
+    for (int it = 0; it < nt; ++it) {
+        if (it == 0 || tile == 0) {
+            // (re)load this warp's 128 rows: lane l holds rows gbase + 32 q + l
+            gbase = row_lo + ib * kIBlock + warp * kGroup;
+            warp_active = gbase < row_act_hi;
+#pragma unroll
+            for (int q = 0; q < kIPT; ++q) {
+                const int i = gbase + 32 * q + lane;
+                const bool act = i < row_act_hi;
+                float4 b = make_float4(kDummyCoord, kDummyCoord, 0.f, 0.f);
+                if (act) b = st.pm[i];
+                nxi[q] = make_float2(-b.x, -b.x);
+                nyi[q] = make_float2(-b.y, -b.y);
+                ri[q] = b.w;
+                const float rs = b.w + rmax;
+                thr[q] = act ? rs * rs : -1.0f;
+                fx[q] = make_float2(0.f, 0.f);
+                fy[q] = make_float2(0.f, 0.f);
+                acc_s[q][threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (excl_len == 0) {
+                w = Window{0, 0, 0, 0};
+            } else if (gbase >= excl_len) {
+                w = Window{gbase - excl_len, gbase, 0, 0};
+            } else {
+                w = Window{0, gbase, n + gbase - excl_len, n};
+            }
+        }
+        if (warp == 0) {                          // producer: refill the stage consumed one iteration ago
+            const int nx = it + kStages - 1;
+            if (nx < nt && lane == 0) {
+                const int ps = nx % kStages;
+                if (it >= 1) mbar_wait(&empty_bar[ps], ((it - 1) / kStages) & 1);
+                mbar_expect_tx(&full_bar[ps], kTileBytes);
+                bulk_g2s(tiles[ps], st.jt + (size_t)ptile * kTileFloats, kTileBytes, &full_bar[ps]);
+                ptile = ptile + 1 == T ? 0 : ptile + 1;
+            }
+            __syncwarp();
+        }
+        const int stage = it % kStages;
+        mbar_wait(&full_bar[stage], (it / kStages) & 1);
+
+        if (warp_active) {
+            const float *tl = tiles[stage];
+            const int jt0 = tile * kTJ;
+#pragma unroll 1
+            for (int sc = 0; sc < kTJ / kSC; ++sc) {
+                const int j0 = jt0 + sc * kSC;
+                const float *px = tl + sc * kSC;
+                const bool special = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
+                float2 sfx[kIPT], sfy[kIPT];
+                bool cand[kIPT];
+#pragma unroll
+                for (int q = 0; q < kIPT; ++q) {
+                    sfx[q] = fx[q];
+                    sfy[q] = fy[q];
+                    cand[q] = special;
+                }
+                if (!special) {
+#pragma unroll
+                    for (int v = 0; v < kSC / 4; ++v) {
+                        const float4 X = *reinterpret_cast<const float4 *>(px + 4 * v);
+                        const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * v);
+                        const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * v);
+#pragma unroll
+                        for (int q = 0; q < kIPT; ++q) {
+                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
+                                          nyi[q], thr[q], fx[q], fy[q], cand[q]);
+                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
+                                          nyi[q], thr[q], fx[q], fy[q], cand[q]);
+                        }
+                    }
+                    ++n_fast;
+                } else {
+                    ++n_exact;
+                }
+#pragma unroll
+                for (int q = 0; q < kIPT; ++q) {
+                    if (__any_sync(0xffffffffu, cand[q])) {
+                        // rare: redo row q of this sub-chunk with the exact predicate
+                        if (!special) ++n_exact;
+                        const int t = 32 * q + lane;
+                        const int row = gbase + t;
+                        const bool act = row < row_act_hi;
+                        int excl = row;
+                        if (limit_first != kGroup) excl = limit_first > 0 ? gbase + (t % limit_first) : -1;
+                        const float xi = -nxi[q].x, yi = -nyi[q].x;
+                        float2 ax = sfx[q], ay = sfy[q];
+#pragma unroll 1
+                        for (int jj = 0; jj < kSC; jj += 2) {
+                            exact_one(st, px, jj, j0 + jj, xi, yi, ri[q], act, row, excl, w, ax.x, ay.x, lane);
+                            exact_one(st, px, jj + 1, j0 + jj + 1, xi, yi, ri[q], act, row, excl, w, ax.y, ay.y, lane);
+                        }
+                        fx[q] = ax;
+                        fy[q] = ay;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+
+        if (warp_active) {                        // fold this tile's sums into the compensated accumulators
+#pragma unroll
+            for (int q = 0; q < kIPT; ++q) {
+                float4 a = acc_s[q][threadIdx.x];
+                two_sum(a.x, a.y, fx[q].x + fx[q].y);
+                two_sum(a.z, a.w, fy[q].x + fy[q].y);
+                acc_s[q][threadIdx.x] = a;
+                fx[q] = make_float2(0.f, 0.f);
+                fy[q] = make_float2(0.f, 0.f);
+            }
+        }
+        if (tile == T - 1 || it == nt - 1) {      // leaving this i-block: flush the partial sums of this segment
+            if (warp_active) {
+                float2 *slab = st.fpart + (size_t)(c + ib) * kIBlock + warp * kGroup + lane;
+#pragma unroll
+                for (int q = 0; q < kIPT; ++q) {
+                    const float4 a = acc_s[q][threadIdx.x];
+                    slab[32 * q] = make_float2(a.x + a.y, a.z + a.w);
+                }
+            }
+        }
+        if (++tile == T) {
+            tile = 0;
+            ++ib;
+        }
+    }
+    if (p.count_stats && lane == 0) {
+        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)n_fast);
+        atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_exact);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish: per-row epilogue of ComputeForces + MoveBodies
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finish_kernel(const DevState st, const StepParams p)
+{
+    const StepDesc &d = *st.desc;
+    const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= d.row_hi) return;
+    const int local = row - d.row_lo;
+    float4 *out_pm = post_pm(st, p.world > 1 ? p.rank : 0);
+    float2 *out_vel = post_vel(st, p.world > 1 ? p.rank : 0);
+    const float4 b = st.pm[row];
+    float2 v = st.vel[row];
+    if (row >= d.row_act_hi) {                    // frozen tail: no thread in either reference kernel
+        out_pm[local] = b;
+        out_vel[local] = v;
+        return;
+    }
+    // force = sum of the segment partials in CTA order
+    const int ib = local / kIBlock, within = local % kIBlock;
+    const long long U = d.units;
+    const int T = d.n_jtiles;
+    const int G = (long long)p.force_grid < U ? p.force_grid : (int)U;
+    const int c_first = unit_owner((long long)ib * T, U, G);
+    const int c_last = unit_owner((long long)(ib + 1) * T - 1, U, G);
+    float fx = 0.f, fy = 0.f;
+    for (int c = c_first; c <= c_last; ++c) {
+        const float2 part = st.fpart[(size_t)(c + ib) * kIBlock + within];
+        fx += part.x;
+        fy += part.y;
+    }
+    // collision bookkeeping in the reference's visit order (src/nbody.cu:215-226)
+    float umass = b.z, uradius = b.w;
+    bool deleted = false;
+    const int h = st.head[row];
+    if (h >= 0) {
+        st.head[row] = -1;
+        int last_key = -1;
+        while (true) {
+            int best_key = 0x7fffffff, best_j = -1;
+            for (int e = h; e >= 0;) {
+                const int2 ce = st.cand[e];
+                const int key = visit_key(d, row, ce.x);
+                if (key > last_key && key < best_key) {
+                    best_key = key;
+                    best_j = ce.x;
+                }
+                e = ce.y;
+            }
+            if (best_j < 0) break;
+            const float4 o = st.pm[best_j];
+            int kind;
+            if (b.z >= o.z) {                     // :215-221
+                umass += o.z;
+                uradius = fmaf(p.growth, o.w, uradius);
+                kind = NB_EV_ABSORB;
+            } else {                              // :222-226
+                deleted = true;
+                kind = NB_EV_KILLED;
+            }
+            if (st.ev_cap > 0) {
+                const unsigned slot = atomicAdd(&st.ctr->ev_count, 1u);
+                if (slot < (unsigned)st.ev_cap) {
+                    st.ev[slot] = EventRec{(int)d.step, row, best_j, ((unsigned)best_key << 1) | (unsigned)kind};
+                } else {
+                    st.ctr->ev_dropped = 1;
+                }
+            }
+            last_key = best_key;
+        }
+    }
+    // velocity + walls (:250-264), position (:288)
+    const float ax = fx * p.grav, ay = fy * p.grav;
+    const float dvx = p.dt * ax, dvy = p.dt * ay;
+    const float W = (float)p.field_w, H = (float)p.field_h;
+    const float nW = (float)(-p.field_w), nH = (float)(-p.field_h);
+    const float tpx = dvx + b.x, tpy = dvy + b.y;
+    if (tpx > W - b.w || tpx < b.w + nW) v.x = -v.x;
+    if (tpy > H - b.w || tpy < b.w + nH) v.y = -v.y;
+    v.x = v.x + dvx;
+    v.y = v.y + dvy;
+    float4 o;
+    o.x = fmaf(p.dt, v.x, b.x);
+    o.y = fmaf(p.dt, v.y, b.y);
+    o.z = deleted ? 0.f : umass;                  // :245
+    o.w = uradius;                                // :246
+    out_pm[local] = o;
+    out_vel[local] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction: count, then scatter (+ plan of the next step in the last CTA)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load_post_pm(const DevState &st, int rpr, int i)
+{
+    const int rk = i / rpr, loc = i - rk * rpr;
+    return post_pm(st, rk)[loc];
+}
+__device__ __forceinline__ float2 load_post_vel(const DevState &st, int rpr, int i)
+{
+    const int rk = i / rpr, loc = i - rk * rpr;
+    return post_vel(st, rk)[loc];
+}
+
+__global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st)
+{
+    __shared__ int s_cnt[kCompactThreads / 32];
+    const int n = st.desc->n, rpr = st.desc->rows_per_rank;
+    const int base = blockIdx.x * kCompactTile;
+    if (base >= n) return;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < kCompactTile / kCompactThreads; ++r) {
+        const int i = base + r * kCompactThreads + threadIdx.x;
+        if (i < n) cnt += load_post_pm(st, rpr, i).z != 0.f ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactThreads / 32; ++k) tot += s_cnt[k];
+        st.tile_count[blockIdx.x] = tot;
+    }
+}
+
+__device__ __forceinline__ void store_body(const DevState &st, int o, const float4 b, const float2 v)
+{
+    st.pm[o] = b;
+    st.vel[o] = v;
+    float *t = st.jt + (size_t)(o >> 8) * kTileFloats + (o & (kTJ - 1));
+    t[0] = b.x;
+    t[kTJ] = b.y;
+    t[2 * kTJ] = b.z;
+    t[3 * kTJ] = b.w;
+}
+__device__ __forceinline__ void store_pad(const DevState &st, int o)
+{
+    float *t = st.jt + (size_t)(o >> 8) * kTileFloats + (o & (kTJ - 1));
+    t[0] = kPadCoord;
+    t[kTJ] = kPadCoord;
+    t[2 * kTJ] = 0.f;
+    t[3 * kTJ] = 0.f;
+}
+
+__device__ __forceinline__ int block_sum(int v, int *s_buf)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactThreads / 32; ++k) tot += s_buf[k];
+    return tot;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState st, const StepParams p)
+{
+    __shared__ int s_buf[kCompactThreads / 32];
+    __shared__ int s_warp[kCompactThreads / 32];
+    __shared__ bool s_last;
+    const int n = st.desc->n, rpr = st.desc->rows_per_rank;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ct = blockIdx.x, base = ct * kCompactTile;
+    if (base < n) {
+        int part = 0;
+        for (int t = threadIdx.x; t < ct; t += kCompactThreads) part += st.tile_count[t];
+        int run = block_sum(part, s_buf);
+        float rmx = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < kCompactTile / kCompactThreads; ++r) {
+            const int i = base + r * kCompactThreads + threadIdx.x;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 v = make_float2(0.f, 0.f);
+            if (i < n) {
+                b = load_post_pm(st, rpr, i);
+                v = load_post_vel(st, rpr, i);
+            }
+            const bool keep = (i < n) && (b.z != 0.f);            // src/nbody.cu:490
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncthreads();
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < kCompactThreads / 32; ++k) {
+                const int cnt = s_warp[k];
+                before += k < warp ? cnt : 0;
+                total += cnt;
+            }
+            if (keep) {
+                store_body(st, run + before + __popc(m & ((1u << lane) - 1u)), b, v);
+                rmx = fmaxf(rmx, b.w);
+            }
+            run += total;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmx = fmaxf(rmx, __shfl_xor_sync(0xffffffffu, rmx, o));
+        if (lane == 0 && rmx > 0.f) atomicMax(&st.res->rmax_bits, __float_as_uint(rmx));
+    }
+    // last CTA to finish plans the next step
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st.res->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int tiles = (n + kCompactTile - 1) / kCompactTile;
+    int part = 0;
+    for (int t = threadIdx.x; t < tiles; t += kCompactThreads) part += __ldcg(&st.tile_count[t]);
+    const int n_new = block_sum(part, s_buf);
+    const int pad_end = (n_new + kTJ - 1) / kTJ * kTJ;
+    for (int o = n_new + threadIdx.x; o < pad_end; o += kCompactThreads) store_pad(st, o);
+    if (threadIdx.x == 0) {
+        const StepDesc old = *st.desc;
+        Counters *c = st.ctr;
+        const long long per_row = old.window_len > 0 ? old.window_len - 1 : 0;
+        c->pairs += (unsigned long long)((long long)(old.row_act_hi - old.row_lo) * per_row);
+        c->candidates += c->cand_count;
+        c->cand_count = 0;
+        c->steps += 1;
+        StepDesc d;
+        plan_fill(d, p, n_new, __uint_as_float(__ldcg(&st.res->rmax_bits)), old.step + 1);
+        *st.desc = d;
+        st.res->rmax_bits = 0u;
+        st.res->ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest / export: the reference's BodiesData block (src/nbody.cu:66-77) <-> the SoA store
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ingest_kernel(const DevState st, const float *__restrict__ block, const int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pad_end = (n + kTJ - 1) / kTJ * kTJ;
+    float r = 0.f;
+    if (i < n) {
+        const float2 pos = reinterpret_cast<const float2 *>(block)[i];
+        const float2 v = reinterpret_cast<const float2 *>(block + 2 * (size_t)n)[i];
+        const float m = block[4 * (size_t)n + i];
+        r = block[5 * (size_t)n + i];
+        store_body(st, i, make_float4(pos.x, pos.y, m, r), v);
+    } else if (i < pad_end) {
+        store_pad(st, i);
+    }
+    if (i < st.cap) st.head[i] = -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((threadIdx.x & 31) == 0 && r > 0.f) atomicMax(&st.res->rmax_bits, __float_as_uint(r));
+}
+
+__global__ void __launch_bounds__(256) export_kernel(const DevState st, float *__restrict__ block, const int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = st.pm[i];
+    reinterpret_cast<float2 *>(block)[i] = make_float2(b.x, b.y);
+    reinterpret_cast<float2 *>(block + 2 * (size_t)n)[i] = st.vel[i];
+    block[4 * (size_t)n + i] = b.z;
+    block[5 * (size_t)n + i] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render: filled discs into an 8-bit image (src/nbody.cu:294-348), bounds-checked
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) render_kernel(const DevState st, const int n, unsigned char *img, const int w,
+                                                     const int h, const int field_w, const int field_h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = st.pm[i];
+    // pixel radius (float) and centre, :310,:318-319 (field_w / field_h are half extents)
+    const float prf = (b.w * (float)w) / (float)field_w;
+    const int dfw = field_w << 1, dfh = field_h << 1;
+    const int cx = (int)(((b.x + (float)field_w) / (float)dfw) * (float)w);
+    const int cy = (int)(((b.y + (float)field_h) / (float)dfh) * (float)h);
+    // bounding box, :323-326 (note the reference's asymmetric >= / > and its float -> int truncation)
+    const int y_min = (float)cy - prf < 0.f ? 0 : (int)((float)cy - prf);
+    const int y_max = (float)cy + prf >= (float)h ? h : (int)((float)cy + prf);
+    const int x_min = (float)cx - prf < 0.f ? 0 : (int)((float)cx - prf);
+    const int x_max = (float)cx + prf > (float)w ? w : (int)((float)cx + prf);
+    const int r2 = (int)(prf * prf);
+    for (int y = y_min; y < y_max; ++y) {
+        for (int x = x_min; x < x_max; ++x) {
+            const int x_sq = (x - cx) * (x - cx), y_sq = (y - cy) * (y - cy);
+            if (x_sq + y_sq <= r2 && x >= 0 && x < w && y >= 0 && y < h) img[(size_t)w * y + x] = 0;   // :344
+        }
+    }
+}
+
+constexpr int kMinCtas = 4;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s)
+{
+    plan_kernel<<<1, 32, 0, s>>>(st, p, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_force(const DevState &st, const StepParams &p, bool packed, cudaStream_t s)
+{
+    if (packed)
+        force_kernel<true, kMinCtas><<<p.force_grid, kForceThreads, 0, s>>>(st, p);
+    else
+        force_kernel<false, kMinCtas><<<p.force_grid, kForceThreads, 0, s>>>(st, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s)
+{
+    const int grid = (st.shard_cap + 255) / 256;
+    finish_kernel<<<grid, 256, 0, s>>>(st, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s)
+{
+    const int grid = (st.cap + kCompactTile - 1) / kCompactTile;
+    count_kernel<<<grid, kCompactThreads, 0, s>>>(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    scatter_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s)
+{
+    const int span = st.cap + kTJ;
+    ingest_kernel<<<(span + 255) / 256, 256, 0, s>>>(st, block, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    export_kernel<<<(n + 255) / 256, 256, 0, s>>>(st, block, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
+                          cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    render_kernel<<<(n + 127) / 128, 128, 0, s>>>(st, n, img, w, h, field_w, field_h);
+    return cudaGetLastError();
+}
+
+int force_occupancy(bool packed, int *regs)
+{
+    int occ = 0;
+    cudaFuncAttributes fa = {};
+    if (packed) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<true, kMinCtas>, kForceThreads, 0);
+        cudaFuncGetAttributes(&fa, force_kernel<true, kMinCtas>);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<false, kMinCtas>, kForceThreads, 0);
+        cudaFuncGetAttributes(&fa, force_kernel<false, kMinCtas>);
+    }
+    if (regs) *regs = fa.numRegs;
+    return occ;
+}
+
+size_t fpart_slabs(int force_grid, int shard_cap)
+{
+    return (size_t)force_grid + (size_t)(shard_cap + kIBlock - 1) / kIBlock + 1;
+}
+
+void plan_host(StepDesc *d, const StepParams *p, int n)
+{
+    plan_fill(*d, *p, n, 0.f, 0u);
+}
+
+}  // namespace nb

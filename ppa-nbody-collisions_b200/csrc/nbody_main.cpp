@@ -1,0 +1,176 @@
+// nbody_main.cpp -- drop-in replacement of the reference executable (main(), src/nbody.cu:373-551)
+// on top of the C ABI in include/nbody_b200.h.
+//
+// With no arguments it behaves like the reference: reads ./nbodyConfig.txt, prints the same banner and
+// echo lines, generates the seed-1024 initial conditions, runs totalIterations steps, writes
+// <imagePath>/iteration_<k>.ppm (binary P5) on the reference's schedule and prints "Time taken".
+// The reference ignores argv (:381-383), so every option below is additive:
+//   --config PATH        config file (default nbodyConfig.txt)
+//   --coverage MODE      reference (default: the exact pair set of src/nbody.cu:182-207) | full (all pairs)
+//   --steps N            override totalIterations
+//   --seed S             override the seed (default 1024, :403)
+//   --scenario KIND      square (default, :401-416) | disc | two-galaxy
+//   --extent R           disc radius for disc / two-galaxy (default: fieldWidth)
+//   --no-images          skip rendering and image files
+//   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
+//   --dump-events PATH   write the collision event list as CSV (step,i,j,kind)
+//   --device D           CUDA device ordinal
+#include <sys/time.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nbody_b200.h"
+
+static double now_s()                                   // jbutil::gettime, include/jbutil.h:98-104
+{
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    return (double)tv.tv_sec + (double)tv.tv_usec * 1E-6;
+}
+
+static void die(nb_ctx *ctx, const char *what, int rc)
+{
+    fprintf(stderr, "%s failed (%d): %s\n", what, rc, nb_last_error(ctx));
+    exit(1);
+}
+
+int main(int argc, char **argv)
+{
+    const double start = now_s();
+    std::string config_path = "nbodyConfig.txt", dump_state, dump_events, scenario = "square";
+    int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
+    unsigned long long seed = 1024;
+    double extent = 0;
+    bool images = true;
+    for (int a = 1; a < argc; ++a) {
+        const std::string opt = argv[a];
+        auto need = [&](const char *name) -> const char * {
+            if (a + 1 >= argc) {
+                fprintf(stderr, "%s needs a value\n", name);
+                exit(2);
+            }
+            return argv[++a];
+        };
+        if (opt == "--config") config_path = need("--config");
+        else if (opt == "--coverage") {
+            const std::string v = need("--coverage");
+            if (v == "reference") coverage = NB_COVERAGE_REFERENCE;
+            else if (v == "full") coverage = NB_COVERAGE_FULL;
+            else { fprintf(stderr, "unknown coverage %s\n", v.c_str()); return 2; }
+        }
+        else if (opt == "--steps") steps_override = atoi(need("--steps"));
+        else if (opt == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
+        else if (opt == "--scenario") scenario = need("--scenario");
+        else if (opt == "--extent") extent = atof(need("--extent"));
+        else if (opt == "--no-images") images = false;
+        else if (opt == "--dump-state") dump_state = need("--dump-state");
+        else if (opt == "--dump-events") dump_events = need("--dump-events");
+        else if (opt == "--device") device = atoi(need("--device"));
+        else { fprintf(stderr, "unknown option %s\n", opt.c_str()); return 2; }
+    }
+
+    fputs("Running simulation with the following settings:\n", stdout);          // :376
+    fflush(stdout);
+    nb_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (nb_config_parse(config_path.c_str(), &cfg, 1) != NB_OK) return 1;        // :377 (exit(1) paths)
+    fputs("=====================\n", stdout);                                     // :378
+    const int n0 = cfg.particleCount;
+    const int total = steps_override >= 0 ? steps_override : cfg.totalIterations;
+    const int every = cfg.save_Image_Every_Xth_Iteration;
+    if (n0 <= 0) {
+        fprintf(stderr, "particleCount must be positive\n");
+        return 1;
+    }
+    printf("Bodies: %d\n", n0);                                                    // :399
+    fflush(stdout);
+
+    std::vector<float> block((size_t)6 * n0);
+    nb_scenario sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.kind = scenario == "disc" ? NB_SCENARIO_DISC : scenario == "two-galaxy" ? NB_SCENARIO_TWO_GALAXY : NB_SCENARIO_SQUARE;
+    sc.n = n0;
+    sc.seed = seed;
+    sc.field_w = cfg.fieldWidth;
+    sc.field_h = cfg.fieldHeight;
+    sc.min_mass = cfg.minRandBodyMass;
+    sc.max_mass = cfg.maxRandBodyMass;
+    sc.min_radius = cfg.minRadius;
+    sc.max_radius = cfg.maxRadius;
+    sc.extent = extent > 0 ? extent : (double)cfg.fieldWidth;
+    if (nb_generate(&sc, block.data()) != NB_OK) {
+        fprintf(stderr, "invalid scenario\n");
+        return 1;
+    }
+
+    nb_params par;
+    memset(&par, 0, sizeof(par));
+    par.n_max = n0;
+    par.dt = cfg.timestep;
+    par.growth = cfg.growthRate;
+    par.field_w = cfg.fieldWidth;
+    par.field_h = cfg.fieldHeight;
+    par.coverage = coverage;
+    par.device = device;
+    par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
+    nb_ctx *ctx = nullptr;
+    int rc = nb_create(&ctx, &par);
+    if (rc != NB_OK) die(nullptr, "nb_create", rc);
+    if ((rc = nb_upload(ctx, block.data(), n0)) != NB_OK) die(ctx, "nb_upload", rc);
+
+    FILE *evf = nullptr;
+    if (!dump_events.empty()) {
+        evf = fopen(dump_events.c_str(), "w");
+        if (!evf) { fprintf(stderr, "cannot open %s\n", dump_events.c_str()); return 1; }
+        fputs("step,i,j,kind\n", evf);
+    }
+    std::vector<nb_event> evbuf(evf ? (1 << 22) : 0);
+    const bool do_images = images && every > 0 && cfg.imgWidth > 0 && cfg.imgHeight > 0;
+    std::vector<uint8_t> img(do_images ? (size_t)cfg.imgWidth * cfg.imgHeight : 0);
+    int pending = -1;                               // iteration whose image waits to be saved
+    for (int it = 0; it < total; ++it) {
+        if ((rc = nb_step(ctx, 1)) != NB_OK) die(ctx, "nb_step", rc);
+        if (do_images) {
+            // the image rendered after iteration k is written during iteration k + 1 (:513-522)
+            if (pending >= 0 && (it - 1) % every == 0) {
+                const std::string path = std::string(cfg.imagePath) + "/iteration_" + std::to_string(pending) + ".ppm";
+                printf("Saving (%dx%d) to disk\n", cfg.imgWidth, cfg.imgHeight);  // :356
+                fflush(stdout);
+                if (nb_write_pgm(path.c_str(), img.data(), cfg.imgWidth, cfg.imgHeight) != NB_OK) {
+                    fprintf(stderr, "Error writing image to file:%s\nEnsure the the folder exists\n", path.c_str());   // :365-369
+                    return 1;
+                }
+                pending = -1;
+            }
+            if (it % every == 0) {                  // :529-539
+                if ((rc = nb_render(ctx, img.data(), cfg.imgWidth, cfg.imgHeight)) != NB_OK) die(ctx, "nb_render", rc);
+                pending = it;
+            }
+        }
+        if (evf && (it % 64 == 63 || it == total - 1)) {
+            int cnt = 0;
+            if ((rc = nb_events(ctx, evbuf.data(), (int)evbuf.size(), &cnt)) != NB_OK) die(ctx, "nb_events", rc);
+            for (int k = 0; k < cnt; ++k)
+                fprintf(evf, "%d,%d,%d,%d\n", evbuf[k].step, evbuf[k].i, evbuf[k].j, evbuf[k].kind);
+        }
+    }
+    if ((rc = nb_sync(ctx)) != NB_OK) die(ctx, "nb_sync", rc);                    // CUDA_SYNC_CHECK, :546
+    if (evf) fclose(evf);
+    if (!dump_state.empty()) {
+        int n = 0;
+        if ((rc = nb_download(ctx, block.data(), n0, &n)) != NB_OK) die(ctx, "nb_download", rc);
+        FILE *f = fopen(dump_state.c_str(), "wb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", dump_state.c_str()); return 1; }
+        const int32_t n32 = n;
+        fwrite(&n32, sizeof(n32), 1, f);
+        fwrite(block.data(), 24, (size_t)n, f);
+        fclose(f);
+    }
+    nb_destroy(ctx);
+    printf("Time taken: %.4f\n", now_s() - start);                                // :548
+    return 0;
+}

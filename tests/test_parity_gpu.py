@@ -1,0 +1,224 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden traces of the
+unmodified reference kernels.  All tests here need a B200 (`-m gpu`).
+
+Bars (BASELINE.json north_star): collision/merge event lists, survivor sets, masses and radii are
+BIT-EXACT; positions and velocities are compared with a stated tolerance because the force sum uses
+rsqrt and a different summation order than the reference:
+    max |dp| <= 1e-5 * field half-width        max |dv| <= 1e-4 * max |v|
+The velocity tolerance is set by the REFERENCE, not by this kernel: the reference adds n float32
+terms into one running sum per body, whose rounding error grows like sqrt(n) * 2^-24 (2e-5 of max |v|
+at n = 131072).  test_force_error_vs_float64_* measures both against a float64 evaluation of the same
+pairs and requires the CUDA path's error to be no larger than the reference arithmetic's own.
+"""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5
+VEL_TOL = 1e-4
+
+
+def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag):
+    assert n_gpu == n_cpu, f"{tag}: n {n_gpu} != {n_cpu}"
+    if n_cpu == 0:
+        return
+    pg, vg, mg, rg = nb.split(got, n_gpu)
+    pc, vc, mc, rc = O.split(cpu, n_cpu)
+    assert np.array_equal(mg.view(np.uint32), mc.view(np.uint32)), f"{tag}: masses not bit-exact"
+    assert np.array_equal(rg.view(np.uint32), rc.view(np.uint32)), f"{tag}: radii not bit-exact"
+    assert np.abs(pg - pc).max() <= POS_TOL * field, f"{tag}: positions off by {np.abs(pg - pc).max()}"
+    vmax = max(float(np.abs(vc).max()), 1e-30)
+    assert np.abs(vg - vc).max() <= VEL_TOL * vmax, f"{tag}: velocities off by {np.abs(vg - vc).max()} of {vmax}"
+
+
+def _compare_events(ev, ev_cpu, tag):
+    assert len(ev) == len(ev_cpu), f"{tag}: {len(ev)} events != {len(ev_cpu)}"
+    assert np.array_equal(ev["i"], ev_cpu["i"]), f"{tag}: event rows"
+    assert np.array_equal(ev["j"], ev_cpu["j"]), f"{tag}: event partners / visit order"
+    assert np.array_equal(ev["kind"], ev_cpu["kind"]), f"{tag}: event kinds"
+
+
+def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=0.1, trace=None, flags=0):
+    sim = nb.Simulation(n0, dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage,
+                        event_capacity=max(64 * n0, 4096), flags=flags)
+    try:
+        sim.upload(block0, n0)
+        cpu = block0.copy()
+        n_cpu = n0
+        par = O.params(dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage)
+        pairs = 0
+        for s in range(steps):
+            if n_cpu == 0:
+                break
+            sim.step(1)
+            n_cpu, stats, ev_cpu = O.step(cpu, n_cpu, par, want_events=True)
+            pairs += stats["pairs"]
+            got, n_gpu = sim.download()
+            if trace is not None:
+                assert n_gpu == trace[s]["n"], f"step {s}: n differs from the reference kernels' golden trace"
+            _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, f"step {s}")
+            ev = sim.events()
+            assert (ev["step"] == s).all()
+            _compare_events(ev, ev_cpu, f"step {s}")
+        st = sim.stats()
+        assert st["pairs"] == pairs, "pairs evaluated"
+        assert st["overflow"] == 0 and st["events_dropped"] == 0
+        return st
+    finally:
+        sim.close()
+
+
+@pytest.fixture(scope="module")
+def gpuref_golden(golden_dir):
+    return json.loads((golden_dir / "gpuref_golden.json").read_text())
+
+
+SMALL = ["small1", "small2", "small5", "small100", "small127", "small128", "small129", "small130", "small200",
+         "small255", "small256", "small257", "small258", "small300", "small383", "small384", "small385",
+         "small1000", "small1500", "dense3000", "dense4096"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_reference_coverage_small(nb, oracle, gpuref_golden, name):
+    """Every edge of the reference's tiling (n < 128, B = 1 with n % 129 slots, frozen tails, ...)."""
+    sc = gpuref_golden["scenarios"][name]
+    block0 = nb.generate(nb.SCENARIO_SQUARE, sc["n0"], seed=sc["seed"], field_w=sc["field"], field_h=sc["field"])
+    _run_side_by_side(nb, oracle, block0, sc["n0"], len(sc["trace"]), nb.COVERAGE_REFERENCE, sc["field"],
+                      dt=sc["dt"], growth=sc["growth"], trace=sc["trace"])
+
+
+def test_reference_coverage_shipped_60_steps(nb, oracle, gpuref_golden):
+    """nbodyConfig.txt as shipped: 60 steps against the oracle and the reference kernels' survivor trace."""
+    sc = gpuref_golden["scenarios"]["shipped"]
+    block0 = nb.generate(nb.SCENARIO_SQUARE, sc["n0"])
+    assert np.array_equal(block0, oracle.init_square(sc["n0"]))
+    st = _run_side_by_side(nb, oracle, block0, sc["n0"], 60, nb.COVERAGE_REFERENCE, sc["field"], trace=sc["trace"])
+    assert st["n"] == 10147
+
+
+@pytest.mark.parametrize("n,field,steps", [(1, 2000, 2), (2, 300, 3), (127, 2000, 4), (128, 2000, 4), (129, 2000, 4),
+                                           (255, 2000, 4), (256, 2000, 4), (257, 2000, 4), (300, 2000, 4),
+                                           (511, 3000, 4), (512, 3000, 4), (513, 3000, 4), (1000, 4000, 6),
+                                           (3000, 12000, 8), (4096, 20000, 8)])
+def test_full_coverage(nb, oracle, n, field, steps):
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field)
+
+
+def test_full_coverage_shipped_20_steps(nb, oracle):
+    block0 = nb.generate(nb.SCENARIO_SQUARE, 16384)
+    _run_side_by_side(nb, oracle, block0, 16384, 20, nb.COVERAGE_FULL, 100000)
+
+
+def test_scalar_force_kernel_and_no_graph(nb, oracle):
+    block0 = nb.generate(nb.SCENARIO_SQUARE, 3000, field_w=12000, field_h=12000)
+    _run_side_by_side(nb, oracle, block0, 3000, 5, nb.COVERAGE_FULL, 12000, flags=nb.FLAG_SCALAR_FORCE | nb.FLAG_NO_GRAPH)
+
+
+def test_disc_scenario_full(nb, oracle):
+    """BASELINE config 2 shape (uniform disc, v = 0), reduced step count."""
+    n = 16384
+    block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5)
+    _run_side_by_side(nb, oracle, block0, n, 10, nb.COVERAGE_FULL, 100000)
+
+
+def test_collapsing_cluster_first_steps(nb, oracle):
+    """BASELINE config 3 shape at 1/8 size and the same surface density: collision-heavy, multi-victim absorbers."""
+    n = 16384
+    block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5 / np.sqrt(8.0), field_w=200000, field_h=200000)
+    st = _run_side_by_side(nb, oracle, block0, n, 4, nb.COVERAGE_FULL, 200000)
+    assert st["candidates"] > n // 2
+
+
+def test_many_steps_in_one_call_matches_single_steps(nb):
+    n = 4096
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=20000, field_h=20000)
+    a = nb.Simulation(n, field_w=20000, field_h=20000, coverage=nb.COVERAGE_FULL)
+    b = nb.Simulation(n, field_w=20000, field_h=20000, coverage=nb.COVERAGE_FULL, flags=nb.FLAG_NO_GRAPH)
+    a.upload(block0, n)
+    b.upload(block0, n)
+    a.step(12)
+    for _ in range(12):
+        b.step(1)
+    ga, na = a.download()
+    gb, nbb = b.download()
+    assert na == nbb and np.array_equal(ga.view(np.uint32), gb.view(np.uint32)), "graph replay is not deterministic"
+    a.close()
+    b.close()
+
+
+def test_rows_at_131072(nb, oracle):
+    """Row sampling: every row depends only on pre-step state, so a sample of rows of the
+    N x N interaction matrix is an exact test of those rows.  Collapsing-cluster density."""
+    n = 131072
+    field = 200000
+    block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5, field_w=field, field_h=field)
+    rng = np.random.default_rng(7)
+    rows = np.unique(np.concatenate([rng.integers(0, n, 1500), np.arange(0, 256), np.arange(n - 256, n)]))
+    par = oracle.params(field_w=field, field_h=field, coverage=oracle.COVERAGE_FULL)
+    want, hits, visited = oracle.rows(block0, n, par, rows)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, event_capacity=4 * n)
+    sim.upload(block0, n)
+    sim.step(1)
+    got, n1 = sim.download()
+    ev = sim.events()
+    st = sim.stats()
+    sim.close()
+    assert st["pairs"] == n * (n - 1)
+    # map sampled pre-step rows to post-compaction slots: survivors keep their order
+    alive_all = np.ones(n, dtype=bool)
+    killed_rows = np.unique(ev["i"][ev["kind"] == nb.EV_KILLED])
+    alive_all[killed_rows] = False
+    assert n1 == int(alive_all.sum())
+    new_index = np.cumsum(alive_all) - 1
+    pg, vg, mg, rg = nb.split(got, n1)
+    alive_s = want[:, 4] != 0
+    assert np.array_equal(alive_s, alive_all[rows]), "survivor flags of the sampled rows"
+    assert np.array_equal(np.bincount(ev["i"], minlength=n)[rows], hits), "events per sampled row"
+    idx = new_index[rows[alive_s]]
+    w = want[alive_s]
+    assert np.array_equal(mg[idx].view(np.uint32), w[:, 4].view(np.uint32))
+    assert np.array_equal(rg[idx].view(np.uint32), w[:, 5].view(np.uint32))
+    assert np.abs(pg[idx] - w[:, 2:4]).max() <= POS_TOL * field
+    assert np.abs(vg[idx] - w[:, 0:2]).max() <= VEL_TOL * np.abs(w[:, 0:2]).max()
+    # accuracy against a float64 evaluation of the same pairs: the CUDA path must not be worse than the
+    # reference's own float32 running sum
+    truth = oracle.rows_dv_f64(block0, n, par, rows)[alive_s]
+    scale = np.abs(truth).max()
+    err_gpu = np.abs(vg[idx].astype(np.float64) - truth).max() / scale
+    err_ref = np.abs(w[:, 0:2].astype(np.float64) - truth).max() / scale
+    print(f"force error vs float64 at n={n}: CUDA {err_gpu:.3e}, reference arithmetic {err_ref:.3e}")
+    assert err_gpu <= max(err_ref, 2e-6)
+
+
+def _force_error_vs_f64(nb, oracle, block0, n, field, coverage):
+    """max |dv - dv_f64| / max |dv_f64| over all surviving rows, for the CUDA path and for the oracle
+    (= the reference's float32 arithmetic), after one step from rest (v = 0, so v' = dv)."""
+    par = oracle.params(field_w=field, field_h=field, coverage=coverage)
+    rows = np.arange(n)
+    truth = oracle.rows_dv_f64(block0, n, par, rows)
+    want, _, _ = oracle.rows(block0, n, par, rows)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=coverage)
+    sim.upload(block0, n)
+    sim.step(1)
+    got, n1 = sim.download()
+    sim.close()
+    keep = want[:, 4] != 0                       # survivors keep their order through the compaction
+    assert n1 == int(keep.sum())
+    _, vg, _, _ = nb.split(got, n1)
+    t = truth[keep]
+    scale = np.abs(t).max()
+    return (np.abs(vg.astype(np.float64) - t).max() / scale,
+            np.abs(want[keep][:, 0:2].astype(np.float64) - t).max() / scale)
+
+
+@pytest.mark.parametrize("coverage", [0, 1])
+def test_force_error_vs_float64_16384(nb, oracle, coverage):
+    n, field = 16384, 100000
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n)
+    err_gpu, err_ref = _force_error_vs_f64(nb, oracle, block0, n, field, coverage)
+    print(f"force error vs float64 at n={n}: CUDA {err_gpu:.3e}, reference arithmetic {err_ref:.3e}")
+    assert err_gpu <= max(err_ref, 2e-6)
