@@ -71,6 +71,9 @@ typedef struct nb_params {
 
 #define NB_FLAG_NO_GRAPH 1    /* launch kernels one by one instead of replaying a CUDA graph        */
 #define NB_FLAG_SCALAR_FORCE 2/* use the scalar-FP32 force kernel instead of the packed f32x2 one   */
+#define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
+                                     see nbody_kernels.cu); 0 = default                                */
+#define NB_FLAG_VARIANT(v) ((v) << NB_FLAG_VARIANT_SHIFT)
 
 typedef struct nb_event {
     int32_t step;             /* step index (0-based, counted since nb_upload)                      */
@@ -92,6 +95,8 @@ typedef struct nb_stats {
     int32_t force_grid;       /* CTAs of the persistent force kernel                                */
     int32_t force_regs;       /* registers per thread of the force kernel                           */
     int32_t row_lo, row_hi;   /* this shard's rows [row_lo, row_hi) of the next step                */
+    int32_t force_threads;    /* threads per CTA of the force kernel                                */
+    int32_t force_variant;    /* force-kernel variant in use                                        */
 } nb_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

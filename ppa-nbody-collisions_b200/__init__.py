@@ -11,13 +11,14 @@ The directory name has a hyphen (it is the reference's name), so import it with
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "lib" / "libnbody_b200.so"
+LIB_PATH = Path(os.environ.get("NBODY_B200_LIB", HERE / "lib" / "libnbody_b200.so"))   # override: kernel experiments only
 DRIVER_PATH = HERE / "bin" / "nbody"
 
 OK = 0
@@ -37,6 +38,11 @@ SYMBOLS = [
 ]
 
 
+def flag_variant(v: int) -> int:
+    """nb_params.flags bits selecting force-kernel variant v (NB_FLAG_VARIANT)."""
+    return v << 8
+
+
 class Params(C.Structure):
     _fields_ = [("n_max", C.c_int), ("dt", C.c_float), ("growth", C.c_float), ("field_w", C.c_int),
                 ("field_h", C.c_int), ("grav", C.c_float), ("coverage", C.c_int), ("device", C.c_int),
@@ -48,7 +54,8 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("pairs", C.c_int64), ("candidates", C.c_int64), ("exact_chunks", C.c_int64),
                 ("fast_chunks", C.c_int64), ("n", C.c_int32), ("overflow", C.c_int32), ("events_dropped", C.c_int32),
                 ("sm_count", C.c_int32), ("force_grid", C.c_int32), ("force_regs", C.c_int32),
-                ("row_lo", C.c_int32), ("row_hi", C.c_int32)]
+                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("force_threads", C.c_int32),
+                ("force_variant", C.c_int32)]
 
 
 class Plan(C.Structure):

@@ -26,7 +26,8 @@ struct nb_ctx {
     int device;
     int sm_count;
     int force_regs;
-    bool packed;
+    int variant;
+    int force_threads;
     cudaStream_t stream;
     cudaGraphExec_t graph;
     bool graph_ready;
@@ -170,8 +171,14 @@ int nb_create(nb_ctx **out, const nb_params *params)
                                                  : (int)std::min<long long>(std::max<long long>(4LL * st.cap, 65536), 1LL << 30);
     st.ev_cap = params->event_capacity > 0 ? params->event_capacity : 0;
 
-    c->packed = !(params->flags & NB_FLAG_SCALAR_FORCE);
-    const int occ = force_occupancy(c->packed, &c->force_regs);
+    c->variant = (params->flags >> NB_FLAG_VARIANT_SHIFT) & 0xf;
+    if (params->flags & NB_FLAG_SCALAR_FORCE) c->variant = 4;
+    if (c->variant >= kForceVariants) {
+        set_err(nullptr, "nb_create: unknown force-kernel variant %d", c->variant);
+        free_all(c);
+        return NB_ERR_INVALID;
+    }
+    const int occ = force_occupancy(c->variant, &c->force_regs, &c->force_threads);
     if (occ <= 0) {
         set_err(nullptr, "nb_create: force kernel does not fit on an SM");
         free_all(c);
@@ -311,7 +318,7 @@ int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
 static int enqueue_step(nb_ctx *c, cudaEvent_t f0, cudaEvent_t f1)
 {
     if (f0) NB_CUDA(c, cudaEventRecord(f0, c->stream));
-    NB_CUDA(c, launch_force(c->st, c->sp, c->packed, c->stream));
+    NB_CUDA(c, launch_force(c->st, c->sp, c->variant, c->stream));
     if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
     NB_CUDA(c, launch_finish(c->st, c->sp, c->stream));
     if (c->sp.world > 1) {
@@ -427,6 +434,8 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->sm_count = c->sm_count;
     out->force_grid = c->sp.force_grid;
     out->force_regs = c->force_regs;
+    out->force_threads = c->force_threads;
+    out->force_variant = c->variant;
     out->row_lo = d.row_lo;
     out->row_hi = d.row_hi;
     return NB_OK;

@@ -22,10 +22,7 @@
 namespace nb {
 
 constexpr int kGroup = 128;                  // rows per visit-order group == reference THREADS_PER_BLOCK (src/nbody.cu:36)
-constexpr int kIPT = 4;                      // rows per lane
-constexpr int kWarps = 4;                    // warps per force CTA; one warp == one 128-row group
-constexpr int kForceThreads = kWarps * 32;
-constexpr int kIBlock = kWarps * kGroup;     // 512 rows per i-block
+constexpr int kIBlock = 512;                 // rows per i-block == rows per force CTA (warps x 32 lanes x rows per lane)
 constexpr int kTJ = 256;                     // j bodies per shared-memory tile
 constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
 constexpr int kTileBytes = kTileFloats * 4;
@@ -50,7 +47,8 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int n_iblocks;                // 512-row i-blocks holding this rank's active rows
     int n_jtiles;                 // T = ceil(n / 256)
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
-    long long units;              // U = n_iblocks * T  (i-block x j-tile work units of this rank)
+    int lg_parts;                 // a work unit is 256 >> lg_parts bodies of one j-tile (0, 1 or 2)
+    long long units;              // U = n_iblocks * T << lg_parts  (work units of this rank)
     float rmax;                   // max radius over live bodies
     unsigned step;                // steps since upload
 };
@@ -116,14 +114,15 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 
 // kernels (nbody_kernels.cu)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
-cudaError_t launch_force(const DevState &st, const StepParams &p, bool packed, cudaStream_t s);
+cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s);
 cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s);
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
                           cudaStream_t s);
-int force_occupancy(bool packed, int *regs);   // resident CTAs per SM of the force kernel
+int force_occupancy(int variant, int *regs, int *threads);   // resident CTAs per SM of the force kernel
+constexpr int kForceVariants = 5;
 size_t fpart_slabs(int force_grid, int shard_cap);   // slabs of 512 float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
 

@@ -29,10 +29,6 @@ __device__ __forceinline__ void fence_barrier_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -100,7 +96,12 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.n_iblocks = (d.row_act_hi - d.row_lo + kIBlock - 1) / kIBlock;
     d.n_jtiles = (n + kTJ - 1) / kTJ;
     d.force_exact = n < 2 * T ? 1 : 0;
-    d.units = (long long)d.n_iblocks * d.n_jtiles;
+    // small problems: split every j-tile into 2 or 4 units so that the static partition over the
+    // force grid stays balanced (a CTA's share is units / grid, rounded up)
+    const long long whole = (long long)d.n_iblocks * d.n_jtiles;
+    const long long grid = p.force_grid > 0 ? p.force_grid : 1;
+    d.lg_parts = whole >= 16 * grid ? 0 : (whole >= 8 * grid ? 1 : 2);
+    d.units = whole << d.lg_parts;
     d.rmax = rmax;
     d.step = step;
 }
@@ -163,8 +164,10 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
         const float2 dx = __fadd2_rn(xs, nxi);
         const float2 dy = __fadd2_rn(ys, nyi);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+#ifndef NB_EXP_NOTEST
         cand |= (d2.x <= thr);
         cand |= (d2.y <= thr);
+#endif
         const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
         const float2 s = __fmul2_rn(__fmul2_rn(inv, inv), __fmul2_rn(inv, ms));
         fx = __ffma2_rn(dx, s, fx);
@@ -224,16 +227,22 @@ __device__ __forceinline__ void exact_one(const DevState &st, const float *tile,
     }
 }
 
-template <bool PACKED, int MINB>
-__global__ void __launch_bounds__(kForceThreads, MINB) force_kernel(const DevState st, const StepParams p)
+// One CTA = WARPS warps x 32 lanes x IPT rows per lane = one 512-row i-block (kIBlock).  The CTA walks a
+// contiguous run of work units (i-block, j-tile, part) of the step's static partition; j-tiles arrive
+// through a kStages-deep ring of 1-D TMA bulk copies (full/empty mbarriers, producer = warp 0 lane 0).
+template <bool PACKED, int WARPS, int IPT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState st, const StepParams p)
 {
+    static_assert(WARPS * 32 * IPT == kIBlock, "one CTA covers one i-block");
+    constexpr int THREADS = WARPS * 32;
+    constexpr int WROWS = 32 * IPT;               // rows per warp (a divisor of the 128-row visit-order group)
     __shared__ __align__(128) float tiles[kStages][kTileFloats];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ __align__(8) unsigned long long empty_bar[kStages];
-    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per tile with a
+    __shared__ unsigned done_cnt[kStages];      // warps that finished the unit in each stage (refill trigger)
+    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per unit with a
     // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one
     // 128-term float sum instead of growing like sqrt(n) as a single running float sum does
-    __shared__ float4 acc_s[kIPT][kForceThreads];
+    __shared__ float4 acc_s[IPT][THREADS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long U = st.desc->units;
@@ -243,56 +252,71 @@ __global__ void __launch_bounds__(kForceThreads, MINB) force_kernel(const DevSta
     const long long u0 = (long long)c * U / G, u1 = (long long)(c + 1) * U / G;
     if (u0 >= u1) return;
     const int nt = (int)(u1 - u0);
-    const int T = st.desc->n_jtiles;
+    const int lgP = st.desc->lg_parts;            // a unit is 256 >> lgP bodies of a j-tile
+    const int TP = st.desc->n_jtiles << lgP;      // units per i-block
     const int n = st.desc->n;
     const int row_lo = st.desc->row_lo, row_act_hi = st.desc->row_act_hi;
     const int excl_len = st.desc->excl_len, limit_first = st.desc->limit_first;
     const bool fexact = st.desc->force_exact != 0;
     const float rmax = st.desc->rmax;
+    const int jw = kTJ >> lgP;                    // bodies per unit
+    const unsigned unit_bytes = (unsigned)kTileBytes >> lgP;
 
-    int ib = (int)(u0 / T);
-    int tile = (int)(u0 - (long long)ib * T);
-    int ptile = tile;                             // next tile the producer issues
+    int ib = (int)(u0 / TP);
+    int v = (int)(u0 - (long long)ib * TP);       // unit index inside the i-block: tile << lgP | part
+
+    auto issue = [&](int stage, int unit) {       // one thread at a time
+        const int tile = unit >> lgP, part = unit & ((1 << lgP) - 1);
+        const float *src = st.jt + (size_t)tile * kTileFloats + part * jw;
+        float *dst = tiles[stage] + part * jw;
+        mbar_expect_tx(&full_bar[stage], unit_bytes);
+        if (lgP == 0) {
+            bulk_g2s(dst, src, kTileBytes, &full_bar[stage]);
+        } else {
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + pl * kTJ, src + pl * kTJ, unit_bytes >> 2, &full_bar[stage]);
+        }
+    };
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kWarps);
+            done_cnt[s] = 0;
         }
         fence_barrier_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int pre = nt < kStages - 1 ? nt : kStages - 1;
+        const int pre = nt < kStages ? nt : kStages;
+        int pv = v;
         for (int k = 0; k < pre; ++k) {
-            mbar_expect_tx(&full_bar[k], kTileBytes);
-            bulk_g2s(tiles[k], st.jt + (size_t)ptile * kTileFloats, kTileBytes, &full_bar[k]);
-            ptile = ptile + 1 == T ? 0 : ptile + 1;
+            issue(k, pv);
+            pv = pv + 1 == TP ? 0 : pv + 1;
         }
     }
 
-    float2 nxi[kIPT], nyi[kIPT], fx[kIPT], fy[kIPT];
-    float thr[kIPT], ri[kIPT];
+    float2 nxi[IPT], nyi[IPT], fx[IPT], fy[IPT];
+    float thr[IPT];
     Window w = {0, 0, 0, 0};
-    int gbase = 0;
+    int wbase = 0, gbase = 0;
     bool warp_active = false;
     unsigned n_fast = 0, n_exact = 0;
 
     for (int it = 0; it < nt; ++it) {
-        if (it == 0 || tile == 0) {
-            // (re)load this warp's 128 rows: lane l holds rows gbase + 32 q + l
-            gbase = row_lo + ib * kIBlock + warp * kGroup;
-            warp_active = gbase < row_act_hi;
+        if (it == 0 || v == 0) {
+            // (re)load this warp's rows: lane l holds rows wbase + 32 q + l; gbase = their 128-row group
+            wbase = row_lo + ib * kIBlock + warp * WROWS;
+            gbase = wbase & ~(kGroup - 1);
+            warp_active = wbase < row_act_hi;
 #pragma unroll
-            for (int q = 0; q < kIPT; ++q) {
-                const int i = gbase + 32 * q + lane;
+            for (int q = 0; q < IPT; ++q) {
+                const int i = wbase + 32 * q + lane;
                 const bool act = i < row_act_hi;
                 float4 b = make_float4(kDummyCoord, kDummyCoord, 0.f, 0.f);
                 if (act) b = st.pm[i];
                 nxi[q] = make_float2(-b.x, -b.x);
                 nyi[q] = make_float2(-b.y, -b.y);
-                ri[q] = b.w;
                 const float rs = b.w + rmax;
                 thr[q] = act ? rs * rs : -1.0f;
                 fx[q] = make_float2(0.f, 0.f);
@@ -307,103 +331,154 @@ __global__ void __launch_bounds__(kForceThreads, MINB) force_kernel(const DevSta
                 w = Window{0, gbase, n + gbase - excl_len, n};
             }
         }
-        if (warp == 0) {                          // producer: refill the stage consumed one iteration ago
-            const int nx = it + kStages - 1;
-            if (nx < nt && lane == 0) {
-                const int ps = nx % kStages;
-                if (it >= 1) mbar_wait(&empty_bar[ps], ((it - 1) / kStages) & 1);
-                mbar_expect_tx(&full_bar[ps], kTileBytes);
-                bulk_g2s(tiles[ps], st.jt + (size_t)ptile * kTileFloats, kTileBytes, &full_bar[ps]);
-                ptile = ptile + 1 == T ? 0 : ptile + 1;
-            }
-            __syncwarp();
-        }
         const int stage = it % kStages;
+#ifndef NB_EXP_NOWAIT
         mbar_wait(&full_bar[stage], (it / kStages) & 1);
+#endif
 
         if (warp_active) {
-            const float *tl = tiles[stage];
-            const int jt0 = tile * kTJ;
+            const int tile = v >> lgP, part = v & ((1 << lgP) - 1);
+            const float *tl = tiles[stage] + part * jw;
+            const int jt0 = tile * kTJ + part * jw;
+            const int nsc = jw / kSC;
+            // Fast pass over the whole unit with no warp-level synchronisation: every 32-body sub-chunk is summed
+            // into fresh accumulators that are folded into the unit sums only if the lane's pre-test saw no
+            // possible hit; flagged (sub-chunk, row) combinations are redone exactly after the pass.
+            // sub-chunks that touch this group's window edge (or all of them when n < 256) are marked up front:
+            // the fast pass still runs over them (straight-line code, no branch) but its sums are dropped
+            unsigned smask = 0;
 #pragma unroll 1
-            for (int sc = 0; sc < kTJ / kSC; ++sc) {
+            for (int sc = 0; sc < nsc; ++sc) {
                 const int j0 = jt0 + sc * kSC;
-                const float *px = tl + sc * kSC;
                 const bool special = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
-                float2 sfx[kIPT], sfy[kIPT];
-                bool cand[kIPT];
+                smask |= (special ? 1u : 0u) << sc;
+                if (special) break;               // at most a handful per step; the rest of the scan is below
+            }
+            if (smask) {
+                smask = 0;
+                for (int sc = 0; sc < nsc; ++sc) {
+                    const int j0 = jt0 + sc * kSC;
+                    const bool special = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
+                    smask |= (special ? 1u : 0u) << sc;
+                }
+            }
+            unsigned cmask = 0;                   // bit sc * IPT + q: row q of this lane must redo sub-chunk sc
+#pragma unroll 2
+            for (int sc = 0; sc < nsc; ++sc) {
+                const float *px = tl + sc * kSC;
+                float2 tfx[IPT], tfy[IPT];
+                bool cand[IPT];
+                const bool special = (smask >> sc) & 1u;
 #pragma unroll
-                for (int q = 0; q < kIPT; ++q) {
-                    sfx[q] = fx[q];
-                    sfy[q] = fy[q];
+                for (int q = 0; q < IPT; ++q) {
+                    tfx[q] = make_float2(0.f, 0.f);
+                    tfy[q] = make_float2(0.f, 0.f);
                     cand[q] = special;
                 }
-                if (!special) {
 #pragma unroll
-                    for (int v = 0; v < kSC / 4; ++v) {
-                        const float4 X = *reinterpret_cast<const float4 *>(px + 4 * v);
-                        const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * v);
-                        const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * v);
+                for (int k4 = 0; k4 < kSC / 4; ++k4) {
+                    const float4 X = *reinterpret_cast<const float4 *>(px + 4 * k4);
+                    const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * k4);
+                    const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * k4);
 #pragma unroll
-                        for (int q = 0; q < kIPT; ++q) {
-                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
-                                          nyi[q], thr[q], fx[q], fy[q], cand[q]);
-                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
-                                          nyi[q], thr[q], fx[q], fy[q], cand[q]);
-                        }
+                    for (int q = 0; q < IPT; ++q) {
+                        pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
+                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                        pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
+                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
                     }
-                    ++n_fast;
-                } else {
-                    ++n_exact;
                 }
 #pragma unroll
-                for (int q = 0; q < kIPT; ++q) {
-                    if (__any_sync(0xffffffffu, cand[q])) {
-                        // rare: redo row q of this sub-chunk with the exact predicate
-                        if (!special) ++n_exact;
-                        const int t = 32 * q + lane;
-                        const int row = gbase + t;
-                        const bool act = row < row_act_hi;
-                        int excl = row;
-                        if (limit_first != kGroup) excl = limit_first > 0 ? gbase + (t % limit_first) : -1;
-                        const float xi = -nxi[q].x, yi = -nyi[q].x;
-                        float2 ax = sfx[q], ay = sfy[q];
-#pragma unroll 1
-                        for (int jj = 0; jj < kSC; jj += 2) {
-                            exact_one(st, px, jj, j0 + jj, xi, yi, ri[q], act, row, excl, w, ax.x, ay.x, lane);
-                            exact_one(st, px, jj + 1, j0 + jj + 1, xi, yi, ri[q], act, row, excl, w, ax.y, ay.y, lane);
-                        }
-                        fx[q] = ax;
-                        fy[q] = ay;
+                for (int q = 0; q < IPT; ++q) {
+                    if (!cand[q]) {
+                        fx[q] = __fadd2_rn(fx[q], tfx[q]);
+                        fy[q] = __fadd2_rn(fy[q], tfy[q]);
                     }
+                    cmask |= (cand[q] ? 1u : 0u) << (sc * IPT + q);
+                }
+            }
+            n_fast += nsc;
+            unsigned redo = __reduce_or_sync(0xffffffffu, cmask);
+            while (redo) {                        // rare: exact predicate for the flagged (sub-chunk, row) combinations
+                const int bit = __ffs(redo) - 1;
+                redo &= redo - 1;
+                const int sc = bit / IPT, q = bit - sc * IPT;
+                const int j0 = jt0 + sc * kSC;
+                const float *px = tl + sc * kSC;
+                const bool mine = (cmask >> bit) & 1u;
+                ++n_exact;
+                float2 nx = nxi[0], ny = nyi[0], ax = fx[0], ay = fy[0];
+#pragma unroll
+                for (int k = 1; k < IPT; ++k)
+                    if (q == k) {
+                        nx = nxi[k];
+                        ny = nyi[k];
+                        ax = fx[k];
+                        ay = fy[k];
+                    }
+                const int row = wbase + 32 * q + lane;
+                const int t = row - gbase;
+                const bool act = mine && row < row_act_hi;
+                int excl = row;
+                if (limit_first != kGroup) excl = limit_first > 0 ? gbase + (t % limit_first) : -1;
+                const float xi = -nx.x, yi = -ny.x;
+                const float ri = act ? st.pm[row].w : 0.f;
+#pragma unroll 1
+                for (int jj = 0; jj < kSC; jj += 2) {
+                    exact_one(st, px, jj, j0 + jj, xi, yi, ri, act, row, excl, w, ax.x, ay.x, lane);
+                    exact_one(st, px, jj + 1, j0 + jj + 1, xi, yi, ri, act, row, excl, w, ax.y, ay.y, lane);
+                }
+#pragma unroll
+                for (int k = 0; k < IPT; ++k)
+                    if (q == k) {
+                        fx[k] = ax;
+                        fy[k] = ay;
+                    }
+            }
+        }
+        // release the stage; the last warp to get here refills it with the unit kStages ahead (no warp ever
+        // waits for another one: the only blocking point is the full barrier above)
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&done_cnt[stage], 1u) == WARPS - 1) {
+                done_cnt[stage] = 0;
+                if (it + kStages < nt) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(stage, (v + kStages) % TP);
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
 
-        if (warp_active) {                        // fold this tile's sums into the compensated accumulators
+        if (warp_active) {                        // fold this unit's sums into the compensated accumulators
 #pragma unroll
-            for (int q = 0; q < kIPT; ++q) {
+            for (int q = 0; q < IPT; ++q) {
                 float4 a = acc_s[q][threadIdx.x];
+#ifdef NB_EXP_NOFOLD
+                if (v == TP - 1 || it == nt - 1) {
+#endif
                 two_sum(a.x, a.y, fx[q].x + fx[q].y);
                 two_sum(a.z, a.w, fy[q].x + fy[q].y);
                 acc_s[q][threadIdx.x] = a;
                 fx[q] = make_float2(0.f, 0.f);
                 fy[q] = make_float2(0.f, 0.f);
+#ifdef NB_EXP_NOFOLD
+                }
+#endif
             }
         }
-        if (tile == T - 1 || it == nt - 1) {      // leaving this i-block: flush the partial sums of this segment
+        if (v == TP - 1 || it == nt - 1) {        // leaving this i-block: flush the partial sums of this segment
             if (warp_active) {
-                float2 *slab = st.fpart + (size_t)(c + ib) * kIBlock + warp * kGroup + lane;
+                float2 *slab = st.fpart + (size_t)(c + ib) * kIBlock + warp * WROWS + lane;
 #pragma unroll
-                for (int q = 0; q < kIPT; ++q) {
+                for (int q = 0; q < IPT; ++q) {
                     const float4 a = acc_s[q][threadIdx.x];
                     slab[32 * q] = make_float2(a.x + a.y, a.z + a.w);
                 }
             }
         }
-        if (++tile == T) {
-            tile = 0;
+        if (++v == TP) {
+            v = 0;
             ++ib;
         }
     }
@@ -434,10 +509,10 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     // force = sum of the segment partials in CTA order
     const int ib = local / kIBlock, within = local % kIBlock;
     const long long U = d.units;
-    const int T = d.n_jtiles;
+    const int TP = d.n_jtiles << d.lg_parts;
     const int G = (long long)p.force_grid < U ? p.force_grid : (int)U;
-    const int c_first = unit_owner((long long)ib * T, U, G);
-    const int c_last = unit_owner((long long)(ib + 1) * T - 1, U, G);
+    const int c_first = unit_owner((long long)ib * TP, U, G);
+    const int c_last = unit_owner((long long)(ib + 1) * TP - 1, U, G);
     float fx = 0.f, fy = 0.f;
     for (int c = c_first; c <= c_last; ++c) {
         const float2 part = st.fpart[(size_t)(c + ib) * kIBlock + within];
@@ -708,7 +783,19 @@ __global__ void __launch_bounds__(128) render_kernel(const DevState st, const in
     }
 }
 
-constexpr int kMinCtas = 4;
+// force-kernel variants (selected by nb_params.flags, see NB_FLAG_VARIANT): occupancy vs rows per lane.
+// Measured on B200 at n = 131072 (profiles/r01_variants.md): 0 is the fastest.
+//   0: packed f32x2, 8 warps x 2 rows/lane, <=  80 registers (3 CTAs = 24 warps per SM)   [default]
+//   1: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
+//   2: packed,       4 warps x 4 rows/lane, <= 128 registers (4 CTAs = 16 warps per SM)
+//   3: packed,       8 warps x 2 rows/lane, <=  64 registers (4 CTAs = 32 warps per SM)
+//   4: scalar FP32,  4 warps x 4 rows/lane (A/B reference for the packed path)
+#define NB_FORCE_VARIANTS(X)     \
+    X(0, true, 8, 2, 3)          \
+    X(1, true, 8, 2, 2)          \
+    X(2, true, 4, 4, 4)          \
+    X(3, true, 8, 2, 4)          \
+    X(4, false, 4, 4, 4)
 
 }  // namespace
 
@@ -721,12 +808,18 @@ cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStre
     return cudaGetLastError();
 }
 
-cudaError_t launch_force(const DevState &st, const StepParams &p, bool packed, cudaStream_t s)
+cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s)
 {
-    if (packed)
-        force_kernel<true, kMinCtas><<<p.force_grid, kForceThreads, 0, s>>>(st, p);
-    else
-        force_kernel<false, kMinCtas><<<p.force_grid, kForceThreads, 0, s>>>(st, p);
+    switch (variant) {
+#define X(ID, PK, W, I, MB)                                                        \
+    case ID:                                                                       \
+        force_kernel<PK, W, I, MB><<<p.force_grid, W * 32, 0, s>>>(st, p);         \
+        break;
+        NB_FORCE_VARIANTS(X)
+#undef X
+    default:
+        return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -769,18 +862,25 @@ cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, 
     return cudaGetLastError();
 }
 
-int force_occupancy(bool packed, int *regs)
+int force_occupancy(int variant, int *regs, int *threads)
 {
     int occ = 0;
     cudaFuncAttributes fa = {};
-    if (packed) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<true, kMinCtas>, kForceThreads, 0);
-        cudaFuncGetAttributes(&fa, force_kernel<true, kMinCtas>);
-    } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<false, kMinCtas>, kForceThreads, 0);
-        cudaFuncGetAttributes(&fa, force_kernel<false, kMinCtas>);
+    int thr = 0;
+    switch (variant) {
+#define X(ID, PK, W, I, MB)                                                                        \
+    case ID:                                                                                       \
+        thr = W * 32;                                                                              \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<PK, W, I, MB>, thr, 0);   \
+        cudaFuncGetAttributes(&fa, force_kernel<PK, W, I, MB>);                                    \
+        break;
+        NB_FORCE_VARIANTS(X)
+#undef X
+    default:
+        return 0;
     }
     if (regs) *regs = fa.numRegs;
+    if (threads) *threads = thr;
     return occ;
 }
 
