@@ -132,7 +132,7 @@ def cpu_baseline(block0: np.ndarray, n: int, budget_s: float = 12.0) -> dict:
                       f"{dt:.1f} s, OpenMP {cores} threads, oracle/nbody_oracle.c)"}
 
 
-def run_reference(args) -> int:
+def run_reference(args, out_stream) -> int:
     """The reference arm: the unmodified ComputeForces/MoveBodies + the reference's per-step
     malloc/H2D/D2H/host compaction, exactly as its main loop does them (oracle/gpu_ref_harness.cu)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -190,11 +190,21 @@ def run_reference(args) -> int:
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "gpu_launches": 0,
                      "note": "oracle/_ref (reference CUDA kernels) unavailable: CPU oracle port on the host cores"})
-    print(json.dumps(base), flush=True)
+    print(json.dumps(base), file=out_stream, flush=True)
     return 0
 
 
+def _claim_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the returned
+    file object is the real stdout, used for the one JSON line."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main() -> int:
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -205,7 +215,7 @@ def main() -> int:
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_stream)
 
     import torch
     import torch.distributed as dist
@@ -332,7 +342,7 @@ def main() -> int:
             out["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(block0, n)
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=out_stream, flush=True)
     sim.close()
     if world > 1:
         dist.destroy_process_group()

@@ -463,6 +463,33 @@ int orc_step(float *block, int n, const orc_params *par,
     return new_n;
 }
 
+/*
+ * generateImage, src/nbody.cu:294-348, for the bodies that exist (i < n; the reference launches a stale grid
+ * without a bound check): filled discs of value 0 into an image pre-filled with 254
+ * (:534).  Float expressions are kept in the reference's order; -ffp-contract=off matches its PTX (no
+ * contraction is possible in these expressions anyway).
+ */
+void orc_render(const float *block, int n, unsigned char *img, int width, int height, int field_w, int field_h)
+{
+    const float *pos = block, *rad = block + 5 * (size_t)n;
+    memset(img, 254, (size_t)width * height);
+    const int dfw = field_w << 1, dfh = field_h << 1;                       /* :314-315 */
+    for (int i = 0; i < n; ++i) {
+        const float pr = (rad[i] * width) / field_w;                          /* :310 */
+        const int cx = (int)(((pos[2 * i] + field_w) / dfw) * width);         /* :318 */
+        const int cy = (int)(((pos[2 * i + 1] + field_h) / dfh) * height);    /* :319 */
+        const int y_min = cy - pr < 0 ? 0 : (int)(cy - pr);                   /* :323-326 */
+        const int y_max = cy + pr >= height ? height : (int)(cy + pr);
+        const int x_min = cx - pr < 0 ? 0 : (int)(cx - pr);
+        const int x_max = cx + pr > width ? width : (int)(cx + pr);
+        const int r2 = (int)(pr * pr);
+        for (int y = y_min; y < y_max; ++y)
+            for (int x = x_min; x < x_max; ++x)
+                if ((x - cx) * (x - cx) + (y - cy) * (y - cy) <= r2 && x >= 0 && x < width && y >= 0 && y < height)
+                    img[(size_t)width * y + x] = 0;                           /* :344 */
+    }
+}
+
 /* FNV-1a-64 over a byte range; used for compact golden fixtures. */
 uint64_t orc_fnv1a64(const void *data, size_t nbytes, uint64_t h)
 {

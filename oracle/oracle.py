@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
                                fp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
         L.orc_rows_dv_f64.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
                                       C.POINTER(C.c_double)]
+        L.orc_render.argtypes = [fp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_step.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.c_void_p, C.c_longlong,
                                C.POINTER(C.c_longlong)]
         L.orc_step.restype = C.c_int
@@ -168,6 +169,13 @@ def rows_dv_f64(block: np.ndarray, n: int, par: OrcParams, row_idx) -> np.ndarra
     lib().orc_rows_dv_f64(_fptr(block), n, C.byref(par), idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx),
                           out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def render(block: np.ndarray, n: int, width: int, height: int, field_w: int, field_h: int) -> np.ndarray:
+    """generateImage (src/nbody.cu:294-348) for the n live bodies: uint8[height, width], background 254, bodies 0."""
+    img = np.zeros((height, width), dtype=np.uint8)
+    lib().orc_render(_fptr(np.ascontiguousarray(block[:6 * n])), n, img.ctypes.data, width, height, field_w, field_h)
+    return img
 
 
 def fnv(a: np.ndarray, h: int = 0) -> int:

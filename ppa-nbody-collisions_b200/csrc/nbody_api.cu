@@ -111,8 +111,9 @@ static void free_all(nb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->comm_ready) nccl_api()->CommDestroy(c->comm);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph_ready) cudaGraphExecDestroy(c->graph);
+    if (c->comm_ready) nccl_api()->CommDestroy(c->comm);
     for (cudaEvent_t e : c->fev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -242,3 +242,56 @@ def test_force_error_vs_float64_16384(nb, oracle, coverage):
     err_gpu, err_ref = _force_error_vs_f64(nb, oracle, block0, n, field, coverage)
     print(f"force error vs float64 at n={n}: CUDA {err_gpu:.3e}, reference arithmetic {err_ref:.3e}")
     assert err_gpu <= max(err_ref, 2e-6)
+
+
+def test_render_matches_reference_rasteriser(nb, oracle):
+    """nb_render against the oracle's restatement of generateImage (src/nbody.cu:294-348)."""
+    n, field = 4096, 20000
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_REFERENCE)
+    sim.upload(block0, n)
+    for w, h in [(256, 256), (300, 200), (64, 512)]:
+        assert np.array_equal(sim.render(w, h), oracle.render(block0, n, w, h, field, field)), (w, h)
+    sim.step(3)
+    got, n1 = sim.download()
+    img = sim.render(512, 512)
+    assert np.array_equal(img, oracle.render(got, n1, 512, 512, field, field))
+    assert set(np.unique(img)) <= {0, 254} and (img == 0).any()
+    sim.close()
+
+
+def test_drop_in_driver(nb, oracle, tmp_path):
+    """The `nbody` executable on a config file: banner, echo, image files on the reference's schedule
+    (src/nbody.cu:513-539), final state equal to the oracle's after the same number of steps."""
+    import subprocess
+    (tmp_path / "imgs").mkdir()
+    (tmp_path / "nbodyConfig.txt").write_text(
+        "particleCount=300\ntotalIterations=8\nsave_Image_Every_Xth_Iteration=3\ntimestep=0.2f\nradiusGrowthRate=0.1f\n"
+        "minRandBodyMass=1e4f\nmaxRandBodyMass=1e17f\nminRadius=50.f\nmaxRadius=200.f\nimgWidth=64\nimgHeight=48\n"
+        "fieldWidth=2000\nfieldHeight=2000\nimagePath=imgs\n")
+    r = subprocess.run([str(nb.DRIVER_PATH), "--dump-state", "state.bin", "--dump-events", "events.csv"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "Running simulation with the following settings:"
+    assert lines[1] == "particleCount=300" and lines[4] == "timestep=0.2" and lines[5] == "growthRate=0.1"
+    assert lines[15] == "=====================" and lines[16] == "Bodies: 300"
+    assert lines[17:-1] == ["Saving (64x48) to disk"] * 3 and lines[-1].startswith("Time taken: ")
+    # images rendered after iterations 0, 3, 6 are written during iterations 1, 4, 7
+    assert sorted(p.name for p in (tmp_path / "imgs").iterdir()) == ["iteration_0.ppm", "iteration_3.ppm", "iteration_6.ppm"]
+    block = oracle.init_square(300, field_w=2000, field_h=2000)
+    par = oracle.params(field_w=2000, field_h=2000)
+    n = 300
+    ev_rows = []
+    for s in range(8):
+        if s == 1:
+            first = (tmp_path / "imgs" / "iteration_0.ppm").read_bytes()
+            assert first == b"P5\n64 48\n255\n" + oracle.render(block, n, 64, 48, 2000, 2000).tobytes()
+        n, _, ev = oracle.step(block, n, par, want_events=True)
+        ev_rows += [f"{s},{e['i']},{e['j']},{e['kind']}" for e in ev]
+    raw = (tmp_path / "state.bin").read_bytes()
+    n_out = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
+    assert n_out == n
+    got = np.frombuffer(raw[4:], dtype=np.float32)
+    _compare_state(nb, oracle, got, n_out, block, n, 2000, "driver final state")
+    assert (tmp_path / "events.csv").read_text().splitlines()[1:] == ev_rows
