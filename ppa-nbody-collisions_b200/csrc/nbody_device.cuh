@@ -23,7 +23,8 @@ namespace nb {
 
 constexpr int kGroup = 128;                  // rows per visit-order group == reference THREADS_PER_BLOCK (src/nbody.cu:36)
 constexpr int kIBlock = 512;                 // rows per i-block == rows per force CTA (warps x 32 lanes x rows per lane)
-constexpr int kTJ = 256;                     // j bodies per shared-memory tile
+constexpr int kTJ = 512;                     // j bodies per shared-memory tile
+constexpr int kMaxLgParts = 3;               // smallest work unit = kTJ >> 3 = 64 bodies
 constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
 constexpr int kTileBytes = kTileFloats * 4;
 constexpr int kSC = 32;                      // j bodies per sub-chunk (granularity of the collision pre-test)

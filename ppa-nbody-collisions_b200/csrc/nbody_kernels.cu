@@ -40,10 +40,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint (ns): sleep in hardware, do not spin
             : "memory");
     } while (!ok);
 }
@@ -96,11 +96,21 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.n_iblocks = (d.row_act_hi - d.row_lo + kIBlock - 1) / kIBlock;
     d.n_jtiles = (n + kTJ - 1) / kTJ;
     d.force_exact = n < 2 * T ? 1 : 0;
-    // small problems: split every j-tile into 2 or 4 units so that the static partition over the
-    // force grid stays balanced (a CTA's share is units / grid, rounded up)
+    // small problems: split every j-tile into 2, 4 or 8 units so that the static partition over the force
+    // grid stays balanced.  Cost model: a CTA's share is ceil(units / grid) units, each costing its bodies
+    // plus a fixed per-unit overhead worth about 12 bodies (barrier wait, vote, compensated fold).
     const long long whole = (long long)d.n_iblocks * d.n_jtiles;
     const long long grid = p.force_grid > 0 ? p.force_grid : 1;
-    d.lg_parts = whole >= 16 * grid ? 0 : (whole >= 8 * grid ? 1 : 2);
+    d.lg_parts = 0;
+    long long best = -1;
+    for (int lg = 0; lg <= kMaxLgParts; ++lg) {
+        const long long per_cta = ((whole << lg) + grid - 1) / grid;
+        const long long cost = per_cta * ((kTJ >> lg) + 12);
+        if (best < 0 || cost < best) {
+            best = cost;
+            d.lg_parts = lg;
+        }
+    }
     d.units = whole << d.lg_parts;
     d.rmax = rmax;
     d.step = step;
@@ -187,43 +197,59 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
     }
 }
 
-// Exact evaluation of one body j for one row: the reference predicate (src/nbody.cu:126-134), its
-// bookkeeping split (hit pairs are excluded from the force sum, :215-226) and candidate emission.
-__device__ __forceinline__ void exact_one(const DevState &st, const float *tile, const int jj, const int j,
-                                          const float xi, const float yi, const float ri, const bool active,
-                                          const int row, const int excl, const Window &w, float &fxl, float &fyl,
-                                          const int lane)
+// Exact evaluation of one 32-body sub-chunk for one row per lane: the reference predicate
+// (src/nbody.cu:126-134), its bookkeeping split (hit pairs are excluded from the force sum, :215-226) and
+// candidate emission.  Hits are collected in a per-lane bit mask first (no warp-level operation inside the
+// j loop) and pushed afterwards: slots of the global candidate list are reserved per warp with one
+// atomicAdd (warp-aggregated), then threaded into the row's chain.
+__device__ __forceinline__ void exact_chunk(const DevState &st, const float *px, const int j0, const float xi,
+                                            const float yi, const float ri, const bool active, const int row,
+                                            const int excl, const Window &w, float2 &ax, float2 &ay, const int lane)
 {
-    const float xj = tile[jj], yj = tile[kTJ + jj], mj = tile[2 * kTJ + jj], rj = tile[3 * kTJ + jj];
-    const float dx = xj - xi, dy = yj - yi;
-    const float d2 = fmaf(dx, dx, dy * dy);
-    const float rs = ri + rj;
-    const float rs2 = rs * rs;
-    const bool hit = d2 <= rs2;
-    const bool in_excl = ((j >= w.a0) & (j < w.b0)) | ((j >= w.a1) & (j < w.b1));
-    const bool valid = active & (j != excl) & !in_excl;
-    const float inv = rsqrt_approx(d2);
-    const float s = (inv * inv) * (inv * mj);
-    if (valid && !hit) {
-        fxl = fmaf(dx, s, fxl);
-        fyl = fmaf(dy, s, fyl);
+    unsigned hits = 0;
+#pragma unroll 2
+    for (int jj = 0; jj < kSC; ++jj) {
+        const float xj = px[jj], yj = px[kTJ + jj], mj = px[2 * kTJ + jj], rj = px[3 * kTJ + jj];
+        const float dx = xj - xi, dy = yj - yi;
+        const float d2 = fmaf(dx, dx, dy * dy);
+        const float rs = ri + rj;
+        const float rs2 = rs * rs;
+        const bool hit = d2 <= rs2;
+        const int j = j0 + jj;
+        const bool in_excl = ((j >= w.a0) & (j < w.b0)) | ((j >= w.a1) & (j < w.b1));
+        const bool valid = active & (j != excl) & !in_excl;
+        const float inv = rsqrt_approx(d2);
+        const float s = (inv * inv) * (inv * mj);
+        if (valid && !hit) {                      // even j -> .x, odd j -> .y: the fast path's lane assignment
+            if (jj & 1) {
+                ax.y = fmaf(dx, s, ax.y);
+                ay.y = fmaf(dy, s, ay.y);
+            } else {
+                ax.x = fmaf(dx, s, ax.x);
+                ay.x = fmaf(dy, s, ay.x);
+            }
+        }
+        hits |= (valid && hit ? 1u : 0u) << jj;
     }
-    const bool push = valid && hit;
-    const unsigned mask = __ballot_sync(0xffffffffu, push);
-    if (mask) {                                   // warp-aggregated reservation in the global candidate list
-        const int leader = __ffs(mask) - 1;
+    unsigned pending = __ballot_sync(0xffffffffu, hits != 0u);
+    while (pending) {
+        const bool push = hits != 0u;
+        const int jj = push ? __ffs(hits) - 1 : 0;
+        hits &= hits - 1u;
+        const int leader = __ffs(pending) - 1;
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&st.ctr->cand_count, (unsigned)__popc(mask));
+        if (lane == leader) base = atomicAdd(&st.ctr->cand_count, (unsigned)__popc(pending));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (push) {
-            const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
+            const unsigned idx = base + __popc(pending & ((1u << lane) - 1u));
             if (idx < (unsigned)st.cand_cap) {
                 const int prev = atomicExch(&st.head[row], (int)idx);
-                st.cand[idx] = make_int2(j, prev);
+                st.cand[idx] = make_int2(j0 + jj, prev);
             } else {
                 st.ctr->overflow_flag = 1;
             }
         }
+        pending = __ballot_sync(0xffffffffu, hits != 0u);
     }
 }
 
@@ -341,73 +367,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
             const float *tl = tiles[stage] + part * jw;
             const int jt0 = tile * kTJ + part * jw;
             const int nsc = jw / kSC;
-            // Fast pass over the whole unit with no warp-level synchronisation: every 32-body sub-chunk is summed
-            // into fresh accumulators that are folded into the unit sums only if the lane's pre-test saw no
-            // possible hit; flagged (sub-chunk, row) combinations are redone exactly after the pass.
-            // sub-chunks that touch this group's window edge (or all of them when n < 256) are marked up front:
-            // the fast pass still runs over them (straight-line code, no branch) but its sums are dropped
-            unsigned smask = 0;
-#pragma unroll 1
-            for (int sc = 0; sc < nsc; ++sc) {
-                const int j0 = jt0 + sc * kSC;
-                const bool special = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
-                smask |= (special ? 1u : 0u) << sc;
-                if (special) break;               // at most a handful per step; the rest of the scan is below
-            }
-            if (smask) {
-                smask = 0;
-                for (int sc = 0; sc < nsc; ++sc) {
-                    const int j0 = jt0 + sc * kSC;
-                    const bool special = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
-                    smask |= (special ? 1u : 0u) << sc;
-                }
-            }
-            unsigned cmask = 0;                   // bit sc * IPT + q: row q of this lane must redo sub-chunk sc
-#pragma unroll 2
-            for (int sc = 0; sc < nsc; ++sc) {
-                const float *px = tl + sc * kSC;
-                float2 tfx[IPT], tfy[IPT];
-                bool cand[IPT];
-                const bool special = (smask >> sc) & 1u;
+            // Fast pass: plain running sums over the whole unit (fx, fy are zero at unit entry) and ONE pre-test
+            // flag per row, no warp-level synchronisation inside.  Only rows whose flag came up (or units that touch
+            // this group's window edge / tiny n) are revisited below.
+            const bool uspecial = fexact | ((jt0 < w.b0) & (jt0 + jw > w.a0)) | ((jt0 < w.b1) & (jt0 + jw > w.a1));
+            bool cand[IPT];
+#pragma unroll
+            for (int q = 0; q < IPT; ++q) cand[q] = uspecial;
+#pragma unroll 8
+            for (int k4 = 0; k4 < jw / 4; ++k4) {
+                const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
+                const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
+                const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
 #pragma unroll
                 for (int q = 0; q < IPT; ++q) {
-                    tfx[q] = make_float2(0.f, 0.f);
-                    tfy[q] = make_float2(0.f, 0.f);
-                    cand[q] = special;
-                }
-#pragma unroll
-                for (int k4 = 0; k4 < kSC / 4; ++k4) {
-                    const float4 X = *reinterpret_cast<const float4 *>(px + 4 * k4);
-                    const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * k4);
-                    const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * k4);
-#pragma unroll
-                    for (int q = 0; q < IPT; ++q) {
-                        pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
-                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
-                        pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
-                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < IPT; ++q) {
-                    if (!cand[q]) {
-                        fx[q] = __fadd2_rn(fx[q], tfx[q]);
-                        fy[q] = __fadd2_rn(fy[q], tfy[q]);
-                    }
-                    cmask |= (cand[q] ? 1u : 0u) << (sc * IPT + q);
+                    pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q], nyi[q],
+                                  thr[q], fx[q], fy[q], cand[q]);
+                    pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q], nyi[q],
+                                  thr[q], fx[q], fy[q], cand[q]);
                 }
             }
             n_fast += nsc;
-            unsigned redo = __reduce_or_sync(0xffffffffu, cmask);
-            while (redo) {                        // rare: exact predicate for the flagged (sub-chunk, row) combinations
-                const int bit = __ffs(redo) - 1;
-                redo &= redo - 1;
-                const int sc = bit / IPT, q = bit - sc * IPT;
-                const int j0 = jt0 + sc * kSC;
-                const float *px = tl + sc * kSC;
-                const bool mine = (cmask >> bit) & 1u;
-                ++n_exact;
+            unsigned rq = 0;
+#pragma unroll
+            for (int q = 0; q < IPT; ++q) rq |= (__any_sync(0xffffffffu, cand[q]) ? 1u : 0u) << q;
+            while (rq) {
+                // rare: row q of some lanes may hold a hit in this unit.  Those lanes drop their unit sums and redo
+                // the unit sub-chunk by sub-chunk: fast sums where the pre-test stays clear, the exact predicate
+                // (with window / self exclusion and candidate emission) where it does not.
+                const int q = __ffs(rq) - 1;
+                rq &= rq - 1;
                 float2 nx = nxi[0], ny = nyi[0], ax = fx[0], ay = fy[0];
+                float th = thr[0];
+                bool mine = cand[0];
 #pragma unroll
                 for (int k = 1; k < IPT; ++k)
                     if (q == k) {
@@ -415,7 +407,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                         ny = nyi[k];
                         ax = fx[k];
                         ay = fy[k];
+                        th = thr[k];
+                        mine = cand[k];
                     }
+                if (mine) {
+                    ax = make_float2(0.f, 0.f);
+                    ay = make_float2(0.f, 0.f);
+                }
                 const int row = wbase + 32 * q + lane;
                 const int t = row - gbase;
                 const bool act = mine && row < row_act_hi;
@@ -424,9 +422,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                 const float xi = -nx.x, yi = -ny.x;
                 const float ri = act ? st.pm[row].w : 0.f;
 #pragma unroll 1
-                for (int jj = 0; jj < kSC; jj += 2) {
-                    exact_one(st, px, jj, j0 + jj, xi, yi, ri, act, row, excl, w, ax.x, ay.x, lane);
-                    exact_one(st, px, jj + 1, j0 + jj + 1, xi, yi, ri, act, row, excl, w, ax.y, ay.y, lane);
+                for (int sc = 0; sc < nsc; ++sc) {
+                    const int j0 = jt0 + sc * kSC;
+                    const float *px = tl + sc * kSC;
+                    float2 tx = make_float2(0.f, 0.f), ty = make_float2(0.f, 0.f);
+                    bool c = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
+                    if (mine) {
+#pragma unroll 1
+                        for (int k4 = 0; k4 < kSC / 4; ++k4) {
+                            const float4 X = *reinterpret_cast<const float4 *>(px + 4 * k4);
+                            const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * k4);
+                            const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * k4);
+                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nx, ny, th, tx, ty, c);
+                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nx, ny, th, tx, ty, c);
+                        }
+                    }
+                    const bool need = mine && c;
+                    if (__any_sync(0xffffffffu, need)) {
+                        ++n_exact;
+                        const bool actx = act && need;
+                        exact_chunk(st, px, j0, xi, yi, ri, actx, row, excl, w, ax, ay, lane);
+                    }
+                    if (mine && !c) {
+                        ax = __fadd2_rn(ax, tx);
+                        ay = __fadd2_rn(ay, ty);
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < IPT; ++k)
@@ -620,7 +640,7 @@ __device__ __forceinline__ void store_body(const DevState &st, int o, const floa
 {
     st.pm[o] = b;
     st.vel[o] = v;
-    float *t = st.jt + (size_t)(o >> 8) * kTileFloats + (o & (kTJ - 1));
+    float *t = st.jt + (size_t)(o / kTJ) * kTileFloats + (o & (kTJ - 1));
     t[0] = b.x;
     t[kTJ] = b.y;
     t[2 * kTJ] = b.z;
@@ -628,7 +648,7 @@ __device__ __forceinline__ void store_body(const DevState &st, int o, const floa
 }
 __device__ __forceinline__ void store_pad(const DevState &st, int o)
 {
-    float *t = st.jt + (size_t)(o >> 8) * kTileFloats + (o & (kTJ - 1));
+    float *t = st.jt + (size_t)(o / kTJ) * kTileFloats + (o & (kTJ - 1));
     t[0] = kPadCoord;
     t[kTJ] = kPadCoord;
     t[2 * kTJ] = 0.f;
@@ -785,16 +805,16 @@ __global__ void __launch_bounds__(128) render_kernel(const DevState st, const in
 
 // force-kernel variants (selected by nb_params.flags, see NB_FLAG_VARIANT): occupancy vs rows per lane.
 // Measured on B200 at n = 131072 (profiles/r01_variants.md): 0 is the fastest.
-//   0: packed f32x2, 8 warps x 2 rows/lane, <=  80 registers (3 CTAs = 24 warps per SM)   [default]
-//   1: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
+//   0: packed f32x2, 8 warps x 2 rows/lane, <=  64 registers (4 CTAs = 32 warps per SM)   [default]
+//   1: packed,       8 warps x 2 rows/lane, <=  80 registers (3 CTAs = 24 warps per SM)
 //   2: packed,       4 warps x 4 rows/lane, <= 128 registers (4 CTAs = 16 warps per SM)
-//   3: packed,       8 warps x 2 rows/lane, <=  64 registers (4 CTAs = 32 warps per SM)
+//   3: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
 //   4: scalar FP32,  4 warps x 4 rows/lane (A/B reference for the packed path)
 #define NB_FORCE_VARIANTS(X)     \
-    X(0, true, 8, 2, 3)          \
-    X(1, true, 8, 2, 2)          \
+    X(0, true, 8, 2, 4)          \
+    X(1, true, 8, 2, 3)          \
     X(2, true, 4, 4, 4)          \
-    X(3, true, 8, 2, 4)          \
+    X(3, true, 8, 2, 2)          \
     X(4, false, 4, 4, 4)
 
 }  // namespace

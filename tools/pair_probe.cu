@@ -24,7 +24,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x)
 }
 
 constexpr int TJ = 256;
-enum Mode { PLAIN = 0, PIPE = 1, NOMUFU = 2, NOTEST = 3, PIPE_NOTEST = 4, PIPE_SPREAD = 5 };
+enum Mode { PLAIN = 0, PIPE = 1, NOMUFU = 2, NOTEST = 3, PIPE_NOTEST = 4, PIPE_SPREAD = 5, SUBCHUNK = 6, SUBCHUNK1 = 7 };
 
 template <int IPT, int MODE>
 struct Stage {
@@ -86,7 +86,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pair(float *out, int reps)
         fx[q] = make_float2(0, 0); fy[q] = make_float2(0, 0); cand[q] = false;
     }
     for (int rep = 0; rep < reps; ++rep) {
-        if (MODE == PIPE || MODE == PIPE_NOTEST) {
+        if (MODE == SUBCHUNK || MODE == SUBCHUNK1) {
+            // the force kernel's structure: fresh sums per 32-body sub-chunk, folded when the pre-test is clear
+            unsigned cmask = 0;
+            const unsigned smask = (unsigned)(reps >> 20);     // runtime zero
+#pragma unroll(MODE == SUBCHUNK ? 2 : 1)
+            for (int sc = 0; sc < TJ / 32; ++sc) {
+                float2 tfx[IPT], tfy[IPT];
+                bool c2[IPT];
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) { tfx[q] = make_float2(0, 0); tfy[q] = make_float2(0, 0); c2[q] = (smask >> sc) & 1u; }
+#pragma unroll
+                for (int j = sc * 32; j < sc * 32 + 32; j += 4) {
+                    Stage<IPT, MODE> st;
+                    st.a(sx, sy, sm, j, nx, ny, thr, c2);
+                    st.b(tfx, tfy);
+                }
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    if (!c2[q]) { fx[q] = __fadd2_rn(fx[q], tfx[q]); fy[q] = __fadd2_rn(fy[q], tfy[q]); }
+                    cmask |= (c2[q] ? 1u : 0u) << (sc * IPT + q);
+                }
+            }
+            if (__reduce_or_sync(0xffffffffu, cmask)) cand[0] = true;
+        } else if (MODE == PIPE || MODE == PIPE_NOTEST) {
             Stage<IPT, MODE> cur, nxt;
             cur.a(sx, sy, sm, 0, nx, ny, thr, cand);
 #pragma unroll 8
@@ -161,15 +184,15 @@ int main()
     run<IPT, MODE, 256, 2>(NAME, out, sms);                     \
     run<IPT, MODE, 256, 3>(NAME, out, sms);                     \
     run<IPT, MODE, 256, 4>(NAME, out, sms);
-    SWEEP(4, PLAIN, "plain")
-    SWEEP(2, PLAIN, "plain")
-    SWEEP(4, PIPE, "pipe")
-    SWEEP(2, PIPE, "pipe")
-    SWEEP(1, PIPE, "pipe")
-    SWEEP(4, NOMUFU, "nomufu")
-    SWEEP(2, NOMUFU, "nomufu")
-    SWEEP(4, NOTEST, "notest")
-    SWEEP(2, PIPE_NOTEST, "pipe_notest")
+    run<2, PLAIN, 256, 3>("plain", out, sms);
+    run<2, SUBCHUNK, 256, 3>("subchunk_u2", out, sms);
+    run<2, SUBCHUNK1, 256, 3>("subchunk_u1", out, sms);
+    run<2, PLAIN, 256, 2>("plain", out, sms);
+    run<2, SUBCHUNK, 256, 2>("subchunk_u2", out, sms);
+    run<2, SUBCHUNK1, 256, 2>("subchunk_u1", out, sms);
+    run<4, PLAIN, 128, 4>("plain", out, sms);
+    run<4, SUBCHUNK, 128, 4>("subchunk_u2", out, sms);
+    run<4, SUBCHUNK1, 128, 4>("subchunk_u1", out, sms);
     CK(cudaFree(out));
     return 0;
 }
