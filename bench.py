@@ -110,6 +110,20 @@ def measured_peaks() -> dict:
         return {}
 
 
+def ncu_traffic_bytes(n: int):
+    """dram__bytes_read + dram__bytes_write of one force-kernel launch from the committed ncu capture of the same
+    workload (profiles/r01_force_1m_ncu.json); None for other sizes."""
+    try:
+        prof = json.loads((ROOT / "profiles" / "r01_force_1m_ncu.json").read_text())["metrics"]
+        if n != N_BODIES:
+            return None
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = prof["dram__bytes_read.sum"], prof["dram__bytes_write.sum"]
+        return float(rd["value"]) * scale[rd["unit"]] + float(wr["value"]) * scale[wr["unit"]]
+    except Exception:
+        return None
+
+
 def cpu_baseline(block0: np.ndarray, n: int, budget_s: float = 12.0) -> dict:
     """The CPU oracle port (oracle/nbody_oracle.c, OpenMP over rows) on a bounded sample of rows of the
     same workload: every row costs n-1 pair evaluations, so rows x (n-1) / time is the port's rate."""
@@ -324,7 +338,10 @@ def main() -> int:
                        "l2": "flushed between timed iterations (256 MiB memset); each step timed by its own CUDA-event pair",
                        "bodies_after": s1["n"]},
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak_tflops, "traffic": None,
+                         "frac": achieved_tflops / peak_tflops, "traffic": ncu_traffic_bytes(n),
+                         "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_force_1m_ncu.json); algorithmic HBM bytes of "
+                                         "the launch are 32 n (one pass over the 16 B/body i rows and j tiles): the kernel is "
+                                         "FP32-issue bound, not HBM bound",
                          "kernel": "force_kernel<packed f32x2>", "ms_per_launch": ms_force_max / args.steps,
                          "flop_per_interaction": FLOP_PER_INTERACTION,
                          "peak_source": f"nameplate FP32 FMA: {sms} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz "
