@@ -26,7 +26,7 @@ POS_TOL = 1e-5
 VEL_TOL = 1e-4
 
 
-def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False):
+def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False, dt=0.2):
     assert n_gpu == n_cpu, f"{tag}: n {n_gpu} != {n_cpu}"
     if n_cpu == 0:
         return
@@ -34,8 +34,10 @@ def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False)
     pc, vc, mc, rc = O.split(cpu, n_cpu)
     assert np.array_equal(mg.view(np.uint32), mc.view(np.uint32)), f"{tag}: masses not bit-exact"
     assert np.array_equal(rg.view(np.uint32), rc.view(np.uint32)), f"{tag}: radii not bit-exact"
-    assert np.abs(pg - pc).max() <= POS_TOL * field, f"{tag}: positions off by {np.abs(pg - pc).max()}"
     vmax = max(float(np.abs(vc).max()), 1e-30)
+    # p' = fma(dt, v', p): a position inherits dt times the velocity error (matters only in violent scenarios)
+    pos_tol = POS_TOL * field + (VEL_TOL if single_step else 100 * VEL_TOL) * vmax * dt
+    assert np.abs(pg - pc).max() <= pos_tol, f"{tag}: positions off by {np.abs(pg - pc).max()} (tolerance {pos_tol})"
     dv = np.abs(vg - vc)
     # single bodies in a close pass amplify the reference's own summation noise step over step (chaos):
     # bound the bulk tightly and the worst body loosely
@@ -69,7 +71,7 @@ def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=
             got, n_gpu = sim.download()
             if trace is not None:
                 assert n_gpu == trace[s]["n"], f"step {s}: n differs from the reference kernels' golden trace"
-            _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, f"step {s}", single_step=resync or s == 0)
+            _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, f"step {s}", single_step=resync or s == 0, dt=dt)
             ev = sim.events()
             assert (ev["step"] == (0 if resync else s)).all()
             _compare_events(ev, ev_cpu, f"step {s}")
