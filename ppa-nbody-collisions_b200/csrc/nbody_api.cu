@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -196,6 +197,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.world = world;
     sp.force_grid = c->sm_count * occ;
     sp.count_stats = 1;
+    sp.lg_parts_override = -1;
+    if (const char *e = getenv("NBODY_B200_LG_PARTS")) sp.lg_parts_override = atoi(e) < 0 ? -1 : (atoi(e) > kMaxLgParts ? kMaxLgParts : atoi(e));   // tuning only
 
     const size_t tiles = (size_t)(st.cap + kTJ - 1) / kTJ + 1;
     const size_t ctiles = (size_t)(st.cap + kCompactTile - 1) / kCompactTile;
@@ -546,6 +549,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.world = params->world > 1 ? params->world : 1;
     sp.rank = params->world > 1 ? params->rank : 0;
     sp.force_grid = force_grid;
+    sp.lg_parts_override = -1;
     StepDesc d;
     plan_host(&d, &sp, n);
     out->n = d.n;

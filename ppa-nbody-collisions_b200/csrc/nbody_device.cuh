@@ -83,6 +83,7 @@ struct StepParams {
     int rank, world;
     int force_grid;
     int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
+    int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
 };
 
 struct DevState {

@@ -96,21 +96,14 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.n_iblocks = (d.row_act_hi - d.row_lo + kIBlock - 1) / kIBlock;
     d.n_jtiles = (n + kTJ - 1) / kTJ;
     d.force_exact = n < 2 * T ? 1 : 0;
-    // small problems: split every j-tile into 2, 4 or 8 units so that the static partition over the force
-    // grid stays balanced.  Cost model: a CTA's share is ceil(units / grid) units, each costing its bodies
-    // plus a fixed per-unit overhead worth about 12 bodies (barrier wait, vote, compensated fold).
+    // Unit size.  Splitting every j-tile into 2, 4 or 8 parts keeps the static partition over the force grid
+    // balanced when there are few tiles per CTA, and a part is also the granularity at which a row that saw a
+    // possible hit is redone, so smaller parts pay off while such rows are frequent.  Thresholds (whole tiles
+    // per CTA) calibrated on B200 with the shipped surface density, profiles/r01_unit_size_sweep.log.
     const long long whole = (long long)d.n_iblocks * d.n_jtiles;
     const long long grid = p.force_grid > 0 ? p.force_grid : 1;
-    d.lg_parts = 0;
-    long long best = -1;
-    for (int lg = 0; lg <= kMaxLgParts; ++lg) {
-        const long long per_cta = ((whole << lg) + grid - 1) / grid;
-        const long long cost = per_cta * ((kTJ >> lg) + 12);
-        if (best < 0 || cost < best) {
-            best = cost;
-            d.lg_parts = lg;
-        }
-    }
+    d.lg_parts = whole < 16 * grid ? 3 : (whole < 100 * grid ? 2 : (whole < 400 * grid ? 1 : 0));
+    if (p.lg_parts_override >= 0) d.lg_parts = p.lg_parts_override;
     d.units = whole << d.lg_parts;
     d.rmax = rmax;
     d.step = step;
@@ -174,10 +167,8 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
         const float2 dx = __fadd2_rn(xs, nxi);
         const float2 dy = __fadd2_rn(ys, nyi);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-#ifndef NB_EXP_NOTEST
         cand |= (d2.x <= thr);
         cand |= (d2.y <= thr);
-#endif
         const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
         const float2 s = __fmul2_rn(__fmul2_rn(inv, inv), __fmul2_rn(inv, ms));
         fx = __ffma2_rn(dx, s, fx);
@@ -253,21 +244,25 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
     }
 }
 
-// One CTA = WARPS warps x 32 lanes x IPT rows per lane = one 512-row i-block (kIBlock).  The CTA walks a
-// contiguous run of work units (i-block, j-tile, part) of the step's static partition; j-tiles arrive
-// through a kStages-deep ring of 1-D TMA bulk copies (full/empty mbarriers, producer = warp 0 lane 0).
+// One CTA = WARPS warps x 32 lanes x IPT rows per lane = one 512-row i-block (kIBlock).  The CTA owns a
+// contiguous run of work units (i-block, j-tile, part) of the step's static partition and walks it in
+// SEGMENTS: the parts of one j-tile that fall into its run (one whole tile when n is large).  A segment is one
+// ring stage: its bodies arrive by 1-D TMA bulk copies completing on an mbarrier, the last warp to finish a
+// stage refills it with the segment kStages ahead.  Inside a segment every part is a checkpoint: its sums are
+// kept only if the row's collision pre-test stayed clear over the part, otherwise the part is redone exactly.
 template <bool PACKED, int WARPS, int IPT, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState st, const StepParams p)
 {
     static_assert(WARPS * 32 * IPT == kIBlock, "one CTA covers one i-block");
+    static_assert(IPT << kMaxLgParts <= 32, "one redo bit per (part, row) of a segment");
     constexpr int THREADS = WARPS * 32;
     constexpr int WROWS = 32 * IPT;               // rows per warp (a divisor of the 128-row visit-order group)
     __shared__ __align__(128) float tiles[kStages][kTileFloats];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ unsigned done_cnt[kStages];      // warps that finished the unit in each stage (refill trigger)
-    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per unit with a
-    // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one
-    // 128-term float sum instead of growing like sqrt(n) as a single running float sum does
+    __shared__ unsigned done_cnt[kStages];      // warps that finished the segment in each stage (refill trigger)
+    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per segment with a
+    // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one short
+    // float sum instead of growing with n as a single running float sum does
     __shared__ float4 acc_s[IPT][THREADS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -277,31 +272,43 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
     if (c >= G) return;
     const long long u0 = (long long)c * U / G, u1 = (long long)(c + 1) * U / G;
     if (u0 >= u1) return;
-    const int nt = (int)(u1 - u0);
-    const int lgP = st.desc->lg_parts;            // a unit is 256 >> lgP bodies of a j-tile
+    const int lgP = st.desc->lg_parts;            // a unit (part) is kTJ >> lgP bodies of a j-tile
+    const int P = 1 << lgP;
     const int TP = st.desc->n_jtiles << lgP;      // units per i-block
     const int n = st.desc->n;
     const int row_lo = st.desc->row_lo, row_act_hi = st.desc->row_act_hi;
     const int excl_len = st.desc->excl_len, limit_first = st.desc->limit_first;
     const bool fexact = st.desc->force_exact != 0;
     const float rmax = st.desc->rmax;
-    const int jw = kTJ >> lgP;                    // bodies per unit
-    const unsigned unit_bytes = (unsigned)kTileBytes >> lgP;
+    const int jw = kTJ >> lgP;                    // bodies per part
+    const int nsc = jw / kSC;                     // 32-body sub-chunks per part
 
     int ib = (int)(u0 / TP);
     int v = (int)(u0 - (long long)ib * TP);       // unit index inside the i-block: tile << lgP | part
+    int left = (int)(u1 - u0);                    // units of the run not yet consumed
+    // parts of the segment that starts at unit v with `rem` units of the run left: up to the end of the tile
+    auto seg_parts = [&](int vv, int rem) { const int to_tile_end = P - (vv & (P - 1)); return rem < to_tile_end ? rem : to_tile_end; };
+    // producer cursor: the segment kStages ahead of the consumer (every warp keeps its own, identical, copy)
+    int pv = v, pleft = left;
 
-    auto issue = [&](int stage, int unit) {       // one thread at a time
-        const int tile = unit >> lgP, part = unit & ((1 << lgP) - 1);
+    auto issue = [&](int stage, int vv, int parts) {   // one thread at a time
+        const int tile = vv >> lgP, part = vv & (P - 1);
         const float *src = st.jt + (size_t)tile * kTileFloats + part * jw;
         float *dst = tiles[stage] + part * jw;
-        mbar_expect_tx(&full_bar[stage], unit_bytes);
-        if (lgP == 0) {
+        const unsigned plane_bytes = (unsigned)(parts * jw) * 4u;
+        mbar_expect_tx(&full_bar[stage], 4u * plane_bytes);
+        if (parts == P && lgP == 0) {
             bulk_g2s(dst, src, kTileBytes, &full_bar[stage]);
         } else {
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + pl * kTJ, src + pl * kTJ, unit_bytes >> 2, &full_bar[stage]);
+            for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + pl * kTJ, src + pl * kTJ, plane_bytes, &full_bar[stage]);
         }
+    };
+    auto advance = [&](int &vv, int &rem) {            // step a cursor over one segment
+        const int parts = seg_parts(vv, rem);
+        rem -= parts;
+        vv += parts;
+        if (vv == TP) vv = 0;
     };
 
     if (threadIdx.x == 0) {
@@ -313,13 +320,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
         fence_barrier_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int pre = nt < kStages ? nt : kStages;
-        int pv = v;
-        for (int k = 0; k < pre; ++k) {
-            issue(k, pv);
-            pv = pv + 1 == TP ? 0 : pv + 1;
-        }
+#pragma unroll 1
+    for (int k = 0; k < kStages; ++k) {               // prologue: fill the ring
+        if (pleft > 0 && threadIdx.x == 0) issue(k, pv, seg_parts(pv, pleft));
+        if (pleft > 0) advance(pv, pleft);
     }
 
     float2 nxi[IPT], nyi[IPT], fx[IPT], fy[IPT];
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
     bool warp_active = false;
     unsigned n_fast = 0, n_exact = 0;
 
-    for (int it = 0; it < nt; ++it) {
+    for (int it = 0; left > 0; ++it) {
         if (it == 0 || v == 0) {
             // (re)load this warp's rows: lane l holds rows wbase + 32 q + l; gbase = their 128-row group
             wbase = row_lo + ib * kIBlock + warp * WROWS;
@@ -357,49 +361,67 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                 w = Window{0, gbase, n + gbase - excl_len, n};
             }
         }
+        const int parts = seg_parts(v, left);
         const int stage = it % kStages;
-#ifndef NB_EXP_NOWAIT
         mbar_wait(&full_bar[stage], (it / kStages) & 1);
-#endif
 
         if (warp_active) {
-            const int tile = v >> lgP, part = v & ((1 << lgP) - 1);
-            const float *tl = tiles[stage] + part * jw;
-            const int jt0 = tile * kTJ + part * jw;
-            const int nsc = jw / kSC;
-            // Fast pass: plain running sums over the whole unit (fx, fy are zero at unit entry) and ONE pre-test
-            // flag per row, no warp-level synchronisation inside.  Only rows whose flag came up (or units that touch
-            // this group's window edge / tiny n) are revisited below.
-            const bool uspecial = fexact | ((jt0 < w.b0) & (jt0 + jw > w.a0)) | ((jt0 < w.b1) & (jt0 + jw > w.a1));
-            bool cand[IPT];
-#pragma unroll
-            for (int q = 0; q < IPT; ++q) cand[q] = uspecial;
-#pragma unroll 8
-            for (int k4 = 0; k4 < jw / 4; ++k4) {
-                const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
-                const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
-                const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
+            const int tile = v >> lgP, part0 = v & (P - 1);
+            // Fast pass: per part, plain running sums and ONE pre-test flag per row, no warp-level
+            // synchronisation inside.  A part's sums are folded into the segment sums only for rows whose flag
+            // stayed clear; the others (a self pair, a real neighbour, a window edge, tiny n) get a redo bit.
+            unsigned cmask = 0;                   // bit pp * IPT + q: row q of this lane must redo part pp
+#pragma unroll 1
+            for (int pp = 0; pp < parts; ++pp) {
+                const float *tl = tiles[stage] + (part0 + pp) * jw;
+                const int jt0 = tile * kTJ + (part0 + pp) * jw;
+                const bool pspecial = fexact | ((jt0 < w.b0) & (jt0 + jw > w.a0)) | ((jt0 < w.b1) & (jt0 + jw > w.a1));
+                float2 tfx[IPT], tfy[IPT];
+                bool cand[IPT];
 #pragma unroll
                 for (int q = 0; q < IPT; ++q) {
-                    pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q], nyi[q],
-                                  thr[q], fx[q], fy[q], cand[q]);
-                    pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q], nyi[q],
-                                  thr[q], fx[q], fy[q], cand[q]);
+                    tfx[q] = make_float2(0.f, 0.f);
+                    tfy[q] = make_float2(0.f, 0.f);
+                    cand[q] = pspecial;
                 }
-            }
-            n_fast += nsc;
-            unsigned rq = 0;
+#pragma unroll 8
+                for (int k4 = 0; k4 < jw / 4; ++k4) {
+                    const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
+                    const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
+                    const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
 #pragma unroll
-            for (int q = 0; q < IPT; ++q) rq |= (__any_sync(0xffffffffu, cand[q]) ? 1u : 0u) << q;
-            while (rq) {
-                // rare: row q of some lanes may hold a hit in this unit.  Those lanes drop their unit sums and redo
-                // the unit sub-chunk by sub-chunk: fast sums where the pre-test stays clear, the exact predicate
-                // (with window / self exclusion and candidate emission) where it does not.
-                const int q = __ffs(rq) - 1;
-                rq &= rq - 1;
+                    for (int q = 0; q < IPT; ++q) {
+                        pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
+                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                        pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
+                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                    }
+                }
+                unsigned bits = 0;
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    if (!cand[q]) {
+                        fx[q] = __fadd2_rn(fx[q], tfx[q]);
+                        fy[q] = __fadd2_rn(fy[q], tfy[q]);
+                    }
+                    bits |= (cand[q] ? 1u : 0u) << q;
+                }
+                cmask |= bits << (pp * IPT);
+            }
+            n_fast += parts * nsc;
+            unsigned redo = __reduce_or_sync(0xffffffffu, cmask);
+            while (redo) {
+                // rare: row q of some lanes may hold a hit in part pp.  Those lanes redo the part sub-chunk by
+                // sub-chunk: fast sums where the pre-test stays clear, the exact predicate (with window / self
+                // exclusion and candidate emission) where it does not.
+                const int bit = __ffs(redo) - 1;
+                redo &= redo - 1;
+                const int pp = bit / IPT, q = bit - pp * IPT;
+                const bool mine = (cmask >> bit) & 1u;
+                const float *tl = tiles[stage] + (part0 + pp) * jw;
+                const int jt0 = tile * kTJ + (part0 + pp) * jw;
                 float2 nx = nxi[0], ny = nyi[0], ax = fx[0], ay = fy[0];
                 float th = thr[0];
-                bool mine = cand[0];
 #pragma unroll
                 for (int k = 1; k < IPT; ++k)
                     if (q == k) {
@@ -408,12 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                         ax = fx[k];
                         ay = fy[k];
                         th = thr[k];
-                        mine = cand[k];
                     }
-                if (mine) {
-                    ax = make_float2(0.f, 0.f);
-                    ay = make_float2(0.f, 0.f);
-                }
                 const int row = wbase + 32 * q + lane;
                 const int t = row - gbase;
                 const bool act = mine && row < row_act_hi;
@@ -426,24 +443,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                     const int j0 = jt0 + sc * kSC;
                     const float *px = tl + sc * kSC;
                     float2 tx = make_float2(0.f, 0.f), ty = make_float2(0.f, 0.f);
-                    bool c = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
+                    bool cc = fexact | ((j0 < w.b0) & (j0 + kSC > w.a0)) | ((j0 < w.b1) & (j0 + kSC > w.a1));
                     if (mine) {
 #pragma unroll 1
                         for (int k4 = 0; k4 < kSC / 4; ++k4) {
                             const float4 X = *reinterpret_cast<const float4 *>(px + 4 * k4);
                             const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * k4);
                             const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * k4);
-                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nx, ny, th, tx, ty, c);
-                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nx, ny, th, tx, ty, c);
+                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nx, ny, th, tx, ty, cc);
+                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nx, ny, th, tx, ty, cc);
                         }
                     }
-                    const bool need = mine && c;
+                    const bool need = mine && cc;
                     if (__any_sync(0xffffffffu, need)) {
                         ++n_exact;
-                        const bool actx = act && need;
-                        exact_chunk(st, px, j0, xi, yi, ri, actx, row, excl, w, ax, ay, lane);
+                        exact_chunk(st, px, j0, xi, yi, ri, act && need, row, excl, w, ax, ay, lane);
                     }
-                    if (mine && !c) {
+                    if (mine && !cc) {
                         ax = __fadd2_rn(ax, tx);
                         ay = __fadd2_rn(ay, ty);
                     }
@@ -456,38 +472,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                     }
             }
         }
-        // release the stage; the last warp to get here refills it with the unit kStages ahead (no warp ever
+        // release the stage; the last warp to get here refills it with the segment kStages ahead (no warp ever
         // waits for another one: the only blocking point is the full barrier above)
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
             if (atomicAdd(&done_cnt[stage], 1u) == WARPS - 1) {
                 done_cnt[stage] = 0;
-                if (it + kStages < nt) {
+                if (pleft > 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(stage, (v + kStages) % TP);
+                    issue(stage, pv, seg_parts(pv, pleft));
                 }
             }
         }
+        if (pleft > 0) advance(pv, pleft);
 
-        if (warp_active) {                        // fold this unit's sums into the compensated accumulators
+        if (warp_active) {                        // fold this segment's sums into the compensated accumulators
 #pragma unroll
             for (int q = 0; q < IPT; ++q) {
                 float4 a = acc_s[q][threadIdx.x];
-#ifdef NB_EXP_NOFOLD
-                if (v == TP - 1 || it == nt - 1) {
-#endif
                 two_sum(a.x, a.y, fx[q].x + fx[q].y);
                 two_sum(a.z, a.w, fy[q].x + fy[q].y);
                 acc_s[q][threadIdx.x] = a;
                 fx[q] = make_float2(0.f, 0.f);
                 fy[q] = make_float2(0.f, 0.f);
-#ifdef NB_EXP_NOFOLD
-                }
-#endif
             }
         }
-        if (v == TP - 1 || it == nt - 1) {        // leaving this i-block: flush the partial sums of this segment
+        left -= parts;
+        v += parts;
+        if (v == TP || left == 0) {               // leaving this i-block: flush the partial sums of this run
             if (warp_active) {
                 float2 *slab = st.fpart + (size_t)(c + ib) * kIBlock + warp * WROWS + lane;
 #pragma unroll
@@ -496,10 +509,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                     slab[32 * q] = make_float2(a.x + a.y, a.z + a.w);
                 }
             }
-        }
-        if (++v == TP) {
-            v = 0;
-            ++ib;
+            if (v == TP) {
+                v = 0;
+                ++ib;
+            }
         }
     }
     if (p.count_stats && lane == 0) {
@@ -805,14 +818,14 @@ __global__ void __launch_bounds__(128) render_kernel(const DevState st, const in
 
 // force-kernel variants (selected by nb_params.flags, see NB_FLAG_VARIANT): occupancy vs rows per lane.
 // Measured on B200 at n = 131072 (profiles/r01_variants.md): 0 is the fastest.
-//   0: packed f32x2, 8 warps x 2 rows/lane, <=  64 registers (4 CTAs = 32 warps per SM)   [default]
-//   1: packed,       8 warps x 2 rows/lane, <=  80 registers (3 CTAs = 24 warps per SM)
+//   0: packed f32x2, 8 warps x 2 rows/lane, <=  80 registers (3 CTAs = 24 warps per SM)   [default]
+//   1: packed,       8 warps x 2 rows/lane, <=  64 registers (4 CTAs = 32 warps per SM)
 //   2: packed,       4 warps x 4 rows/lane, <= 128 registers (4 CTAs = 16 warps per SM)
 //   3: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
 //   4: scalar FP32,  4 warps x 4 rows/lane (A/B reference for the packed path)
 #define NB_FORCE_VARIANTS(X)     \
-    X(0, true, 8, 2, 4)          \
-    X(1, true, 8, 2, 3)          \
+    X(0, true, 8, 2, 3)          \
+    X(1, true, 8, 2, 4)          \
     X(2, true, 4, 4, 4)          \
     X(3, true, 8, 2, 2)          \
     X(4, false, 4, 4, 4)

@@ -1,0 +1,19 @@
+for n in 131072 262144 524288; do for lg in 0 1 2 3; do echo -n "n=$n lgP=$lg: "; NBODY_B200_LG_PARTS=$lg python - <<PY
+import sys
+sys.path.insert(0,'.')
+import numpy as np
+import __graft_entry__ as G
+nb=G.load_package()
+n=$n
+R=1e5*np.sqrt(n/16384.0); field=int(R)
+block0=nb.generate(nb.SCENARIO_DISC,n,extent=R,field_w=field,field_h=field)
+for var in (0,1):
+    sim=nb.Simulation(n,field_w=field,field_h=field,coverage=nb.COVERAGE_FULL,flags=nb.flag_variant(var))
+    sim.upload(block0,n); sim.step(3); sim.sync()
+    s0=sim.stats(); tot,frc=sim.step_timed(5,force=True); s1=sim.stats()
+    pairs=s1['pairs']-s0['pairs']
+    print('v%d force_ms=%.4f frac=%.3f exact=%d fast=%d |'%(var,frc/5,pairs*20/(frc*1e-3)/74.45e12,s1['exact_chunks']-s0['exact_chunks'],s1['fast_chunks']-s0['fast_chunks']),end=' ')
+    sim.close()
+print()
+PY
+done; done
