@@ -349,7 +349,7 @@ def main() -> int:
                                         f"profiles/r01_fp32_probe.jsonl)",
                          "share_of_step": ms_force_max / ms_total_max},
             "clocks": clocks,
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": (3 if world == 1 else 4) * args.steps,
             "wall_s_timed_region": wall,
             "force": {"grid": s1["force_grid"], "regs": s1["force_regs"],
                       "fast_chunks": s1["fast_chunks"] - s0["fast_chunks"], "exact_chunks": s1["exact_chunks"] - s0["exact_chunks"]},

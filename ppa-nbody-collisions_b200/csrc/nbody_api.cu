@@ -230,6 +230,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.res, 0, sizeof(StepResult), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.head, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(st.tile_count, 0, sizeof(int) * ctiles, c->stream);
     if (e == cudaSuccess) e = launch_plan(st, sp, 0, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
@@ -253,6 +254,7 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
     NB_CUDA(c, cudaSetDevice(c->device));
     if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
+    NB_CUDA(c, cudaMemsetAsync(c->st.tile_count, 0, sizeof(int) * ((size_t)(c->st.cap + kCompactTile - 1) / kCompactTile), c->stream));
     NB_CUDA(c, launch_ingest(c->st, (const float *)c->dev_block, n, c->stream));
     NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
     // the caller may reuse `bodies` as soon as we return

@@ -3,7 +3,7 @@
 // HBM layout (all arrays owned by the context, allocated once for n_max bodies):
 //   pm   [cap]          float4 {x, y, m, r}   current compacted bodies (the i side, 16 B coalesced)
 //   vel  [cap]          float2 {vx, vy}
-//   jt   [tiles][4][256] float                 the same bodies as planar 4 KB j-tiles {x[256] y[256] m[256] r[256]}:
+//   jt   [tiles][4][512] float                 the same bodies as planar 8 KB j-tiles {x[512] y[512] m[512] r[512]}:
 //                                              one 1-D TMA bulk copy per tile; the last tile is padded with
 //                                              benign bodies (far away, m = 0, r = 0)
 //   post [world][shard_cap*24 B]               uncompacted post-step rows, one chunk per rank:
@@ -46,9 +46,9 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int row_act_hi;               // min(row_hi, n_active), >= row_lo
     int rows_per_rank;            // rows per rank this step (multiple of 512)
     int n_iblocks;                // 512-row i-blocks holding this rank's active rows
-    int n_jtiles;                 // T = ceil(n / 256)
+    int n_jtiles;                 // T = ceil(n / kTJ)
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
-    int lg_parts;                 // a work unit is 256 >> lg_parts bodies of one j-tile (0, 1 or 2)
+    int lg_parts;                 // a work unit is kTJ >> lg_parts bodies of one j-tile (0 .. kMaxLgParts)
     long long units;              // U = n_iblocks * T << lg_parts  (work units of this rank)
     float rmax;                   // max radius over live bodies
     unsigned step;                // steps since upload

@@ -524,11 +524,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
 // ------------------------------------------------------------------------------------------------
 // finish: per-row epilogue of ComputeForces + MoveBodies
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finish_kernel(const DevState st, const StepParams p)
+__device__ __forceinline__ bool finish_row(const DevState &st, const StepParams &p, const StepDesc &d, const int row)
 {
-    const StepDesc &d = *st.desc;
-    const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= d.row_hi) return;
+    if (row >= d.row_hi) return false;
     const int local = row - d.row_lo;
     float4 *out_pm = post_pm(st, p.world > 1 ? p.rank : 0);
     float2 *out_vel = post_vel(st, p.world > 1 ? p.rank : 0);
@@ -537,7 +535,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     if (row >= d.row_act_hi) {                    // frozen tail: no thread in either reference kernel
         out_pm[local] = b;
         out_vel[local] = v;
-        return;
+        return b.z != 0.f;
     }
     // force = sum of the segment partials in CTA order
     const int ib = local / kIBlock, within = local % kIBlock;
@@ -609,6 +607,20 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     o.w = uradius;                                // :246
     out_pm[local] = o;
     out_vel[local] = v;
+    return o.z != 0.f;
+}
+
+__global__ void __launch_bounds__(256) finish_kernel(const DevState st, const StepParams p)
+{
+    const StepDesc &d = *st.desc;
+    const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool survives = finish_row(st, p, d, row);
+    if (p.world <= 1) {
+        // single GPU: the survivor count of the compaction tiles is taken here (saves the count kernel);
+        // tile_count is zero on entry (upload / the previous scatter clear it)
+        const unsigned m = __ballot_sync(0xffffffffu, survives);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st.tile_count[row / kCompactTile], __popc(m));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,6 +748,7 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
     int part = 0;
     for (int t = threadIdx.x; t < tiles; t += kCompactThreads) part += __ldcg(&st.tile_count[t]);
     const int n_new = block_sum(part, s_buf);
+    for (int t = threadIdx.x; t < tiles; t += kCompactThreads) st.tile_count[t] = 0;   // finish_kernel adds into them
     const int pad_end = (n_new + kTJ - 1) / kTJ * kTJ;
     for (int o = n_new + threadIdx.x; o < pad_end; o += kCompactThreads) store_pad(st, o);
     if (threadIdx.x == 0) {
@@ -866,9 +879,11 @@ cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t 
 cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s)
 {
     const int grid = (st.cap + kCompactTile - 1) / kCompactTile;
-    count_kernel<<<grid, kCompactThreads, 0, s>>>(st);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (p.world > 1) {            // the other ranks' rows were counted on their GPUs: recount everything here
+        count_kernel<<<grid, kCompactThreads, 0, s>>>(st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     scatter_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
     return cudaGetLastError();
 }
