@@ -13,6 +13,8 @@
 //   --extent R           disc radius for disc / two-galaxy (default: fieldWidth)
 //   --no-images          skip rendering and image files
 //   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
+//   --resume PATH        start from a --dump-state file instead of generating initial conditions
+//                        (checkpoint / resume: the reference has none)
 //   --dump-events PATH   write the collision event list as CSV (step,i,j,kind)
 //   --device D           CUDA device ordinal
 #include <sys/time.h>
@@ -41,7 +43,7 @@ static void die(nb_ctx *ctx, const char *what, int rc)
 int main(int argc, char **argv)
 {
     const double start = now_s();
-    std::string config_path = "nbodyConfig.txt", dump_state, dump_events, scenario = "square";
+    std::string config_path = "nbodyConfig.txt", dump_state, dump_events, resume, scenario = "square";
     int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
     unsigned long long seed = 1024;
     double extent = 0;
@@ -69,6 +71,7 @@ int main(int argc, char **argv)
         else if (opt == "--no-images") images = false;
         else if (opt == "--dump-state") dump_state = need("--dump-state");
         else if (opt == "--dump-events") dump_events = need("--dump-events");
+        else if (opt == "--resume") resume = need("--resume");
         else if (opt == "--device") device = atoi(need("--device"));
         else { fprintf(stderr, "unknown option %s\n", opt.c_str()); return 2; }
     }
@@ -79,7 +82,17 @@ int main(int argc, char **argv)
     memset(&cfg, 0, sizeof(cfg));
     if (nb_config_parse(config_path.c_str(), &cfg, 1) != NB_OK) return 1;        // :377 (exit(1) paths)
     fputs("=====================\n", stdout);                                     // :378
-    const int n0 = cfg.particleCount;
+    int n0 = cfg.particleCount;
+    std::vector<float> resumed;
+    if (!resume.empty()) {
+        FILE *f = fopen(resume.c_str(), "rb");
+        int32_t n32 = 0;
+        if (!f || fread(&n32, sizeof(n32), 1, f) != 1 || n32 <= 0) { fprintf(stderr, "cannot read %s\n", resume.c_str()); return 1; }
+        resumed.resize((size_t)6 * n32);
+        if (fread(resumed.data(), 24, (size_t)n32, f) != (size_t)n32) { fprintf(stderr, "%s is truncated\n", resume.c_str()); return 1; }
+        fclose(f);
+        n0 = n32;
+    }
     const int total = steps_override >= 0 ? steps_override : cfg.totalIterations;
     const int every = cfg.save_Image_Every_Xth_Iteration;
     if (n0 <= 0) {
@@ -102,7 +115,9 @@ int main(int argc, char **argv)
     sc.min_radius = cfg.minRadius;
     sc.max_radius = cfg.maxRadius;
     sc.extent = extent > 0 ? extent : (double)cfg.fieldWidth;
-    if (nb_generate(&sc, block.data()) != NB_OK) {
+    if (!resumed.empty()) {
+        block = resumed;
+    } else if (nb_generate(&sc, block.data()) != NB_OK) {
         fprintf(stderr, "invalid scenario\n");
         return 1;
     }

@@ -383,3 +383,18 @@ def test_full_size_properties(nb, oracle, n, scenario):
     again, n2 = sim.download()
     sim.close()
     assert n2 == n1 and np.array_equal(again.view(np.uint32), got.view(np.uint32))
+
+
+def test_driver_checkpoint_resume(nb, tmp_path):
+    """--dump-state / --resume: 4 + 4 steps from a checkpoint end in the same bits as 8 steps in one run."""
+    import subprocess
+    cfg = ("particleCount=2000\ntotalIterations=8\nsave_Image_Every_Xth_Iteration=100\ntimestep=0.2f\nradiusGrowthRate=0.1f\n"
+           "minRandBodyMass=1e4f\nmaxRandBodyMass=1e17f\nminRadius=50.f\nmaxRadius=200.f\nimgWidth=32\nimgHeight=32\n"
+           "fieldWidth=8000\nfieldHeight=8000\nimagePath=.\n")
+    (tmp_path / "nbodyConfig.txt").write_text(cfg)
+    run = lambda *a: subprocess.run([str(nb.DRIVER_PATH), "--no-images", *a], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert run("--dump-state", "full.bin").returncode == 0
+    assert run("--steps", "4", "--dump-state", "half.bin").returncode == 0
+    r = run("--steps", "4", "--resume", "half.bin", "--dump-state", "resumed.bin")
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "resumed.bin").read_bytes() == (tmp_path / "full.bin").read_bytes()
