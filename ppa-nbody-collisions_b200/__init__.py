@@ -32,7 +32,7 @@ UNIQUE_ID_BYTES = 128
 # every symbol include/nbody_b200.h declares
 SYMBOLS = [
     "nb_create", "nb_destroy", "nb_last_error", "nb_version", "nb_upload", "nb_download", "nb_num_bodies",
-    "nb_step", "nb_step_timed", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
+    "nb_step", "nb_step_timed", "nb_step_profile", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_plan_host", "nb_render", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
     "nb_rng_fval_range", "nb_generate",
 ]
@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
     L.nb_num_bodies.argtypes = [vp, ip]
     L.nb_step.argtypes = [vp, C.c_int]
     L.nb_step_timed.argtypes = [vp, C.c_int, fp, fp]
+    L.nb_step_profile.argtypes = [vp, C.c_int, fp]
     L.nb_sync.argtypes = [vp]
     L.nb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nb_events.argtypes = [vp, vp, C.c_int, ip]
@@ -246,6 +247,12 @@ class Simulation:
         tot, frc = C.c_float(0), C.c_float(0)
         self._check("nb_step_timed", lib().nb_step_timed(self._h, n_steps, C.byref(tot), C.byref(frc) if force else None))
         return tot.value, frc.value
+
+    def step_profile(self, n_steps: int = 1) -> dict:
+        """Per-kernel device times in ms summed over n_steps (no graph): force, finish, allgather, compact."""
+        ms = (C.c_float * 4)()
+        self._check("nb_step_profile", lib().nb_step_profile(self._h, n_steps, ms))
+        return {"force": ms[0], "finish": ms[1], "allgather": ms[2], "compact": ms[3]}
 
     def sync(self):
         self._check("nb_sync", lib().nb_sync(self._h))

@@ -320,18 +320,24 @@ int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
     return check_flags(c, ctr);
 }
 
-// one step's launches on the context's stream; f0/f1 (optional) bracket the force kernel
-static int enqueue_step(nb_ctx *c, cudaEvent_t f0, cudaEvent_t f1)
+// one step's launches on the context's stream; f0/f1 (optional) bracket the force kernel, marks (optional,
+// 5 events) separate force | finish | allgather | compaction
+static int enqueue_step(nb_ctx *c, cudaEvent_t f0, cudaEvent_t f1, cudaEvent_t *marks = nullptr)
 {
     if (f0) NB_CUDA(c, cudaEventRecord(f0, c->stream));
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[0], c->stream));
     NB_CUDA(c, launch_force(c->st, c->sp, c->variant, c->stream));
     if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[1], c->stream));
     NB_CUDA(c, launch_finish(c->st, c->sp, c->stream));
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[2], c->stream));
     if (c->sp.world > 1) {
         const size_t chunk = (size_t)c->st.shard_cap * 24;
         NB_NCCL(c, nccl_api()->AllGather(c->st.post + (size_t)c->sp.rank * chunk, c->st.post, chunk, ncclChar, c->comm, c->stream));
     }
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[3], c->stream));
     NB_CUDA(c, launch_compact(c->st, c->sp, c->stream));
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[4], c->stream));
     return NB_OK;
 }
 
@@ -418,6 +424,29 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
         sum += ms;
     }
     *ms_force = sum;
+    return NB_OK;
+}
+
+int nb_step_profile(nb_ctx *c, int n_steps, float ms[4])
+{
+    int rc = step_precheck(c, n_steps);
+    if (rc != NB_OK) return rc;
+    if (!ms) return NB_ERR_INVALID;
+    while ((int)c->fev.size() < 5) {
+        cudaEvent_t e;
+        NB_CUDA(c, cudaEventCreate(&e));
+        c->fev.push_back(e);
+    }
+    for (int k = 0; k < 4; ++k) ms[k] = 0.f;
+    for (int s = 0; s < n_steps; ++s) {
+        if ((rc = enqueue_step(c, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
+        NB_CUDA(c, cudaEventSynchronize(c->fev[4]));
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.f;
+            NB_CUDA(c, cudaEventElapsedTime(&t, c->fev[k], c->fev[k + 1]));
+            ms[k] += t;
+        }
+    }
     return NB_OK;
 }
 
