@@ -3,7 +3,8 @@
 // One step = force (ComputeForces' O(n^2) pair loop, src/nbody.cu:182-242)
 //          -> finish (collision bookkeeping :215-226,245-246, velocity + walls :250-264, MoveBodies :277-292)
 //          -> [allgather of the post-step rows when sharded]
-//          -> count + scatter (the host compaction of :488-510 as a stable device compaction) + plan of the next step.
+//          -> [count when sharded] + scatter (the host compaction of :488-510 as a stable device compaction)
+//             + plan of the next step in the last CTA.
 //
 // Compiled with -fmad=false: every fused multiply-add below is written explicitly and sits exactly where
 // the reference's PTX has one (SURVEY.md 8a "arithmetic contract"); the force sum itself uses rsqrt and a
