@@ -162,7 +162,14 @@ int nb_create(nb_ctx **out, const nb_params *params)
     c->device = params->device;
     c->sm_count = prop.multiProcessorCount;
     c->err[0] = 0;
-    NB_CUDA(nullptr, cudaSetDevice(c->device));
+    {
+        const cudaError_t e = cudaSetDevice(c->device);
+        if (e != cudaSuccess) {
+            set_err(nullptr, "nb_create: cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+            delete c;
+            return NB_ERR_CUDA;
+        }
+    }
 
     const int world = params->world > 1 ? params->world : 1;
     DevState &st = c->st;

@@ -24,7 +24,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x)
 }
 
 constexpr int TJ = 256;
-enum Mode { PLAIN = 0, PIPE = 1, NOMUFU = 2, NOTEST = 3, PIPE_NOTEST = 4, PIPE_SPREAD = 5, SUBCHUNK = 6, SUBCHUNK1 = 7 };
+enum Mode { PLAIN = 0, PIPE = 1, NOMUFU = 2, NOTEST = 3, PIPE_NOTEST = 4, PIPE_SPREAD = 5, SUBCHUNK = 6, SUBCHUNK1 = 7, HYB_ACC = 8, HYB_ACC_S = 9, HYB_ALLB = 10, SCALAR = 11, HYB_D2 = 12 };
 
 template <int IPT, int MODE>
 struct Stage {
@@ -43,9 +43,21 @@ struct Stage {
         for (int q = 0; q < IPT; ++q)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                dx[q][u] = __fadd2_rn(xs[u], make_float2(nx[q], nx[q]));
-                dy[q][u] = __fadd2_rn(ys[u], make_float2(ny[q], ny[q]));
-                const float2 d2 = __ffma2_rn(dx[q][u], dx[q][u], __fmul2_rn(dy[q][u], dy[q][u]));
+                float2 d2;
+                if (MODE == SCALAR) {
+                    dx[q][u] = make_float2(xs[u].x + nx[q], xs[u].y + nx[q]);
+                    dy[q][u] = make_float2(ys[u].x + ny[q], ys[u].y + ny[q]);
+                    d2 = make_float2(fmaf(dx[q][u].x, dx[q][u].x, dy[q][u].x * dy[q][u].x), fmaf(dx[q][u].y, dx[q][u].y, dy[q][u].y * dy[q][u].y));
+                } else if (MODE == HYB_D2) {
+                    dx[q][u] = __fadd2_rn(xs[u], make_float2(nx[q], nx[q]));
+                    dy[q][u] = __fadd2_rn(ys[u], make_float2(ny[q], ny[q]));
+                    const float2 t = __fmul2_rn(dy[q][u], dy[q][u]);
+                    d2 = make_float2(fmaf(dx[q][u].x, dx[q][u].x, t.x), fmaf(dx[q][u].y, dx[q][u].y, t.y));
+                } else {
+                    dx[q][u] = __fadd2_rn(xs[u], make_float2(nx[q], nx[q]));
+                    dy[q][u] = __fadd2_rn(ys[u], make_float2(ny[q], ny[q]));
+                    d2 = __ffma2_rn(dx[q][u], dx[q][u], __fmul2_rn(dy[q][u], dy[q][u]));
+                }
                 if (MODE != NOTEST && MODE != PIPE_NOTEST) {
                     cand[q] |= (d2.x <= thr[q]);
                     cand[q] |= (d2.y <= thr[q]);
@@ -62,9 +74,25 @@ struct Stage {
         for (int q = 0; q < IPT; ++q)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const float2 s = __fmul2_rn(__fmul2_rn(inv[q][u], inv[q][u]), __fmul2_rn(inv[q][u], m[u]));
-                fx[q] = __ffma2_rn(dx[q][u], s, fx[q]);
-                fy[q] = __ffma2_rn(dy[q][u], s, fy[q]);
+                if (MODE == HYB_ACC) {             // packed products, scalar accumulates
+                    const float2 s = __fmul2_rn(__fmul2_rn(inv[q][u], inv[q][u]), __fmul2_rn(inv[q][u], m[u]));
+                    fx[q].x = fmaf(dx[q][u].x, s.x, fx[q].x); fx[q].y = fmaf(dx[q][u].y, s.y, fx[q].y);
+                    fy[q].x = fmaf(dy[q][u].x, s.x, fy[q].x); fy[q].y = fmaf(dy[q][u].y, s.y, fy[q].y);
+                } else if (MODE == HYB_ACC_S) {    // packed inv^2, scalar inv*m, s and accumulates
+                    const float2 i2 = __fmul2_rn(inv[q][u], inv[q][u]);
+                    const float s0 = i2.x * (inv[q][u].x * m[u].x), s1 = i2.y * (inv[q][u].y * m[u].y);
+                    fx[q].x = fmaf(dx[q][u].x, s0, fx[q].x); fx[q].y = fmaf(dx[q][u].y, s1, fx[q].y);
+                    fy[q].x = fmaf(dy[q][u].x, s0, fy[q].x); fy[q].y = fmaf(dy[q][u].y, s1, fy[q].y);
+                } else if (MODE == HYB_ALLB || MODE == SCALAR) {   // stage B fully scalar
+                    const float s0 = (inv[q][u].x * inv[q][u].x) * (inv[q][u].x * m[u].x);
+                    const float s1 = (inv[q][u].y * inv[q][u].y) * (inv[q][u].y * m[u].y);
+                    fx[q].x = fmaf(dx[q][u].x, s0, fx[q].x); fx[q].y = fmaf(dx[q][u].y, s1, fx[q].y);
+                    fy[q].x = fmaf(dy[q][u].x, s0, fy[q].x); fy[q].y = fmaf(dy[q][u].y, s1, fy[q].y);
+                } else {
+                    const float2 s = __fmul2_rn(__fmul2_rn(inv[q][u], inv[q][u]), __fmul2_rn(inv[q][u], m[u]));
+                    fx[q] = __ffma2_rn(dx[q][u], s, fx[q]);
+                    fy[q] = __ffma2_rn(dy[q][u], s, fy[q]);
+                }
             }
     }
 };
@@ -184,15 +212,13 @@ int main()
     run<IPT, MODE, 256, 2>(NAME, out, sms);                     \
     run<IPT, MODE, 256, 3>(NAME, out, sms);                     \
     run<IPT, MODE, 256, 4>(NAME, out, sms);
-    run<2, PLAIN, 256, 3>("plain", out, sms);
-    run<2, SUBCHUNK, 256, 3>("subchunk_u2", out, sms);
-    run<2, SUBCHUNK1, 256, 3>("subchunk_u1", out, sms);
-    run<2, PLAIN, 256, 2>("plain", out, sms);
-    run<2, SUBCHUNK, 256, 2>("subchunk_u2", out, sms);
-    run<2, SUBCHUNK1, 256, 2>("subchunk_u1", out, sms);
-    run<4, PLAIN, 128, 4>("plain", out, sms);
-    run<4, SUBCHUNK, 128, 4>("subchunk_u2", out, sms);
-    run<4, SUBCHUNK1, 128, 4>("subchunk_u1", out, sms);
+#define SW(MODE, NAME) run<2, MODE, 256, 3>(NAME, out, sms); run<2, MODE, 256, 2>(NAME, out, sms); run<4, MODE, 128, 4>(NAME, out, sms);
+    SW(PLAIN, "plain")
+    SW(HYB_ACC, "hyb_acc")
+    SW(HYB_ACC_S, "hyb_acc_s")
+    SW(HYB_ALLB, "hyb_allb")
+    SW(HYB_D2, "hyb_d2")
+    SW(SCALAR, "scalar")
     CK(cudaFree(out));
     return 0;
 }
