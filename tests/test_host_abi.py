@@ -152,3 +152,33 @@ def test_driver_binary_is_built(nb):
     assert nb.DRIVER_PATH.exists(), "ppa-nbody-collisions_b200/bin/nbody (drop-in driver) was not built"
     out = subprocess.run([str(nb.DRIVER_PATH), "--bogus"], capture_output=True, text=True)
     assert out.returncode == 2 and "unknown option" in out.stderr
+
+
+def test_vec2_header_matches_reference_semantics(tmp_path, host_golden):
+    """include/nb_vec2.h (API-compatible Vec2f / Vec2<T>) against operator results produced by the reference's
+    own include/vec2f.h (tools/make_golden_host.py, same expressions)."""
+    src = tmp_path / "v.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include "nb_vec2.h"
+static uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+int main() {
+    Vec2f a(3.f, -4.f), b(0.5f, 7.f);
+    Vec2f c = a * 3.f; Vec2f d = a / 3.f; Vec2f e = a * b; Vec2f f = a + b; Vec2f g = a - b; Vec2f h = -a;
+    Vec2f s(2.5f); Vec2f k = 2.f * b;
+    printf("%08x %08x\n", bits(c.X), bits(c.Y)); printf("%08x %08x\n", bits(d.X), bits(d.Y));
+    printf("%08x %08x\n", bits(e.X), bits(e.Y)); printf("%08x %08x\n", bits(f.X), bits(f.Y));
+    printf("%08x %08x\n", bits(g.X), bits(g.Y)); printf("%08x %08x\n", bits(h.X), bits(h.Y));
+    printf("%08x %08x\n", bits(s.X), bits(s.Y)); printf("%08x %08x\n", bits(k.X), bits(k.Y));
+    printf("%08x\n", bits(a.length())); printf("%08x\n", bits(Vec2f(1e-3f, 7.f).length()));
+    printf("%zu\n", sizeof(Vec2f));
+    Vec2<double> q(1.0, 2.0); q /= 3.0; q += Vec2<double>(1.0); q *= 2.0; a[1] = 9.f;
+    return (q.X > 0 && a.Element[1] == 9.f && sizeof(Vec2<double>) == 16) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "v"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [l for l in out if l] == host_golden["vec2f"]
