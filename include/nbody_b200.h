@@ -67,10 +67,16 @@ typedef struct nb_params {
     int   rank;               /* this context's shard, 0 <= rank < world                            */
     int   world;              /* number of shards (GPUs); <= 1 means single GPU                     */
     int   flags;              /* NB_FLAG_*                                                          */
+    int   sort_min_n;         /* smallest n that uses the sorted order, 0 -> NB_SORT_MIN_N_DEFAULT   */
 } nb_params;
 
 #define NB_FLAG_NO_GRAPH 1    /* launch kernels one by one instead of replaying a CUDA graph        */
 #define NB_FLAG_SCALAR_FORCE 2/* use the scalar-FP32 force kernel instead of the packed f32x2 one   */
+#define NB_FLAG_NO_SORT 4     /* never use the cell-sorted shadow order.  By default, with NB_COVERAGE_FULL and
+                                 n >= sort_min_n, every step runs on a Morton-cell-sorted copy of the bodies so that
+                                 the collision pre-test is skipped for (rows, j part) pairs whose bounding boxes are
+                                 apart; results keep the bodies' own order, events and survivors are unchanged     */
+#define NB_SORT_MIN_N_DEFAULT 98304
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
 #define NB_FLAG_VARIANT(v) ((v) << NB_FLAG_VARIANT_SHIFT)
@@ -97,6 +103,7 @@ typedef struct nb_stats {
     int32_t row_lo, row_hi;   /* this shard's rows [row_lo, row_hi) of the next step                */
     int32_t force_threads;    /* threads per CTA of the force kernel                                */
     int32_t force_variant;    /* force-kernel variant in use                                        */
+    int64_t culled_parts;     /* j parts that ran without the collision pre-test (sorted stream)    */
 } nb_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

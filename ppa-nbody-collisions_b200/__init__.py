@@ -25,7 +25,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_CANDIDATE_OVERFLOW, ERR_COMM, ERR_IO, ERR_EVENT_OVERFLOW = -1, -2, -3, -4, -5, -6, -7
 COVERAGE_REFERENCE, COVERAGE_FULL = 0, 1
 EV_ABSORB, EV_KILLED = 0, 1
-FLAG_NO_GRAPH, FLAG_SCALAR_FORCE = 1, 2
+FLAG_NO_GRAPH, FLAG_SCALAR_FORCE, FLAG_NO_SORT = 1, 2, 4
 SCENARIO_SQUARE, SCENARIO_DISC, SCENARIO_TWO_GALAXY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 
@@ -47,7 +47,7 @@ class Params(C.Structure):
     _fields_ = [("n_max", C.c_int), ("dt", C.c_float), ("growth", C.c_float), ("field_w", C.c_int),
                 ("field_h", C.c_int), ("grav", C.c_float), ("coverage", C.c_int), ("device", C.c_int),
                 ("candidate_capacity", C.c_int), ("event_capacity", C.c_int), ("rank", C.c_int),
-                ("world", C.c_int), ("flags", C.c_int)]
+                ("world", C.c_int), ("flags", C.c_int), ("sort_min_n", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -55,7 +55,7 @@ class Stats(C.Structure):
                 ("fast_chunks", C.c_int64), ("n", C.c_int32), ("overflow", C.c_int32), ("events_dropped", C.c_int32),
                 ("sm_count", C.c_int32), ("force_grid", C.c_int32), ("force_regs", C.c_int32),
                 ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("force_threads", C.c_int32),
-                ("force_variant", C.c_int32)]
+                ("force_variant", C.c_int32), ("culled_parts", C.c_int64)]
 
 
 class Plan(C.Structure):
@@ -189,10 +189,11 @@ class Simulation:
 
     def __init__(self, n_max: int, dt: float = 0.2, growth: float = 0.1, field_w: int = 100000, field_h: int = 100000,
                  coverage: int = COVERAGE_REFERENCE, device: int = 0, event_capacity: int = 0,
-                 candidate_capacity: int = 0, rank: int = 0, world: int = 1, flags: int = 0, grav: float = 0.0):
+                 candidate_capacity: int = 0, rank: int = 0, world: int = 1, flags: int = 0, grav: float = 0.0,
+                 sort_min_n: int = 0):
         self._h = C.c_void_p()
         self.params = Params(n_max, np.float32(dt), np.float32(growth), field_w, field_h, np.float32(grav), coverage,
-                             device, candidate_capacity, event_capacity, rank, world, flags)
+                             device, candidate_capacity, event_capacity, rank, world, flags, sort_min_n)
         rc = lib().nb_create(C.byref(self._h), C.byref(self.params))
         if rc != OK:
             self._h = C.c_void_p()

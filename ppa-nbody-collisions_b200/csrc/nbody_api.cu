@@ -30,8 +30,12 @@ struct nb_ctx {
     int variant;
     int force_threads;
     cudaStream_t stream;
-    cudaGraphExec_t graph;
-    bool graph_ready;
+    cudaGraphExec_t graph[2];          // [0] plain step, [1] step + rebuild of the cell-sorted shadow order
+    bool graph_ready[2];
+    StepParams sp_plain;               // sp with the sorted order switched off (what graph[0] bakes in)
+    volatile int *host_n;              // pinned + mapped: live body count, written by the device every step
+    cudaEvent_t ring[16];              // bounds how far the host runs ahead when it picks a graph per step
+    unsigned long long ring_pos;
     cudaEvent_t ev0, ev1;
     std::vector<cudaEvent_t> fev;     // per-step force-kernel brackets of nb_step_timed
     ncclComm_t comm;
@@ -113,13 +117,18 @@ static void free_all(nb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->graph_ready) cudaGraphExecDestroy(c->graph);
+    for (int k = 0; k < 2; ++k)
+        if (c->graph_ready[k]) cudaGraphExecDestroy(c->graph[k]);
+    for (cudaEvent_t e : c->ring)
+        if (e) cudaEventDestroy(e);
+    if (c->host_n) cudaFreeHost((void *)c->host_n);
     if (c->comm_ready) nccl_api()->CommDestroy(c->comm);
     for (cudaEvent_t e : c->fev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
-    void *ptrs[] = {c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.head, c->st.cand,
+    void *ptrs[] = {c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
+                    c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -204,6 +213,13 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.world = world;
     sp.force_grid = c->sm_count * occ;
     sp.count_stats = 1;
+    // the cell-sorted order pays for itself from about 1e5 bodies on; it needs all-pairs coverage (the reference's
+    // excluded windows are defined by body index) and is sized in only if the capacity can ever reach the threshold
+    sp.sort_min_n = 0;
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT)) {
+        const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
+        if (st.cap >= min_n) sp.sort_min_n = min_n;
+    }
     sp.lg_parts_override = -1;
     if (const char *e = getenv("NBODY_B200_LG_PARTS")) sp.lg_parts_override = atoi(e) < 0 ? -1 : (atoi(e) > kMaxLgParts ? kMaxLgParts : atoi(e));   // tuning only
 
@@ -222,6 +238,15 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.vel, sizeof(float2) * (size_t)st.cap);
     NB_ALLOC(st.jt, (size_t)kTileBytes * tiles);
     NB_ALLOC(st.post, (size_t)world * st.shard_cap * 24);
+    if (sp.sort_min_n > 0) {
+        NB_ALLOC(st.jts, sizeof(float) * kSortedTileFloats * tiles);
+        for (int k = 0; k < 2; ++k) {
+            NB_ALLOC(st.skey[k], sizeof(unsigned) * (size_t)st.cap);
+            NB_ALLOC(st.sidx[k], sizeof(int) * (size_t)st.cap);
+        }
+        NB_ALLOC(st.shist, sizeof(unsigned) * sort_hist_entries(st.cap));
+        NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
+    }
     NB_ALLOC(st.fpart, sizeof(float2) * kIBlock * fpart_slabs(sp.force_grid, st.shard_cap));
     NB_ALLOC(st.head, sizeof(int) * (size_t)st.cap);
     NB_ALLOC(st.cand, sizeof(int2) * (size_t)st.cand_cap);
@@ -232,7 +257,15 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.ctr, sizeof(Counters));
     NB_ALLOC(c->dev_block, (size_t)24 * st.cap);
 #undef NB_ALLOC
+    c->sp_plain = sp;
+    c->sp_plain.sort_min_n = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->host_n, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *c->host_n = 0;
+        e = cudaHostGetDevicePointer((void **)&st.host_n, (void *)c->host_n, 0);
+    }
+    for (int k = 0; k < 16 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ring[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.res, 0, sizeof(StepResult), c->stream);
@@ -259,11 +292,14 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
         return NB_ERR_CAPACITY;
     }
     NB_CUDA(c, cudaSetDevice(c->device));
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ring_pos = 0;
     if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.tile_count, 0, sizeof(int) * ((size_t)(c->st.cap + kCompactTile - 1) / kCompactTile), c->stream));
     NB_CUDA(c, launch_ingest(c->st, (const float *)c->dev_block, n, c->stream));
     NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
+    if (c->sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, c->sp, c->stream));
     // the caller may reuse `bodies` as soon as we return
     NB_CUDA(c, cudaStreamSynchronize(c->stream));
     return NB_OK;
@@ -329,41 +365,75 @@ int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
 
 // one step's launches on the context's stream; f0/f1 (optional) bracket the force kernel, marks (optional,
 // 5 events) separate force | finish | allgather | compaction
-static int enqueue_step(nb_ctx *c, cudaEvent_t f0, cudaEvent_t f1, cudaEvent_t *marks = nullptr)
+static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEvent_t f1, cudaEvent_t *marks = nullptr)
 {
     if (f0) NB_CUDA(c, cudaEventRecord(f0, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[0], c->stream));
-    NB_CUDA(c, launch_force(c->st, c->sp, c->variant, c->stream));
+    NB_CUDA(c, launch_force(c->st, sp, c->variant, c->stream));
     if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[1], c->stream));
-    NB_CUDA(c, launch_finish(c->st, c->sp, c->stream));
+    NB_CUDA(c, launch_finish(c->st, sp, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[2], c->stream));
     if (c->sp.world > 1) {
         const size_t chunk = (size_t)c->st.shard_cap * 24;
         NB_NCCL(c, nccl_api()->AllGather(c->st.post + (size_t)c->sp.rank * chunk, c->st.post, chunk, ncclChar, c->comm, c->stream));
     }
     if (marks) NB_CUDA(c, cudaEventRecord(marks[3], c->stream));
-    NB_CUDA(c, launch_compact(c->st, c->sp, c->stream));
+    // a sort-capable context always runs the count kernel (it exits at once when finish already counted): the
+    // step may have run on the sorted order even if THIS graph will not rebuild it
+    NB_CUDA(c, launch_compact(c->st, sp, c->sp.sort_min_n > 0, c->stream));
+    if (sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, sp, c->stream));   // shadow order of the next step
     if (marks) NB_CUDA(c, cudaEventRecord(marks[4], c->stream));
     return NB_OK;
 }
 
-static int ensure_graph(nb_ctx *c)
+static int ensure_graph(nb_ctx *c, int which)
 {
-    if (c->graph_ready) return NB_OK;
+    if (c->graph_ready[which]) return NB_OK;
     cudaGraph_t g = nullptr;
     NB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(c, nullptr, nullptr);
+    int rc = enqueue_step(c, which ? c->sp : c->sp_plain, nullptr, nullptr);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     if (rc != NB_OK) {
         if (g) cudaGraphDestroy(g);
         return rc;
     }
     NB_CUDA(c, e);
-    e = cudaGraphInstantiate(&c->graph, g, 0);
+    e = cudaGraphInstantiate(&c->graph[which], g, 0);
     cudaGraphDestroy(g);
     NB_CUDA(c, e);
-    c->graph_ready = true;
+    c->graph_ready[which] = true;
+    return NB_OK;
+}
+
+// n_steps steps through the CUDA graphs (or plain launches with NB_FLAG_NO_GRAPH).  A sort-capable context
+// picks, per step, the graph that also rebuilds the sorted order while the live body count (mirrored to pinned
+// host memory by the device) is at or above the threshold, and the lean graph once it has fallen below.  n
+// only shrinks, so a stale (too large) count can only pick the richer graph, whose extra kernels then exit at
+// once; either graph is correct after either.  To keep the count reasonably fresh the host stays at most 16
+// steps ahead of the device.
+static int run_steps(nb_ctx *c, int n_steps)
+{
+    int rc;
+    const bool sortable = c->sp.sort_min_n > 0;
+    for (int s = 0; s < n_steps; ++s) {
+        int which = 0;
+        if (sortable) {
+            cudaEvent_t &slot = c->ring[c->ring_pos % 16];
+            if (c->ring_pos >= 16) NB_CUDA(c, cudaEventSynchronize(slot));
+            which = *c->host_n >= c->sp.sort_min_n ? 1 : 0;
+        }
+        if (c->par.flags & NB_FLAG_NO_GRAPH) {
+            if ((rc = enqueue_step(c, which ? c->sp : c->sp_plain, nullptr, nullptr)) != NB_OK) return rc;
+        } else {
+            if ((rc = ensure_graph(c, which)) != NB_OK) return rc;
+            NB_CUDA(c, cudaGraphLaunch(c->graph[which], c->stream));
+        }
+        if (sortable) {
+            NB_CUDA(c, cudaEventRecord(c->ring[c->ring_pos % 16], c->stream));
+            ++c->ring_pos;
+        }
+    }
     return NB_OK;
 }
 
@@ -382,13 +452,7 @@ int nb_step(nb_ctx *c, int n_steps)
 {
     int rc = step_precheck(c, n_steps);
     if (rc != NB_OK) return rc;
-    if (c->par.flags & NB_FLAG_NO_GRAPH) {
-        for (int s = 0; s < n_steps; ++s)
-            if ((rc = enqueue_step(c, nullptr, nullptr)) != NB_OK) return rc;
-    } else {
-        if ((rc = ensure_graph(c)) != NB_OK) return rc;
-        for (int s = 0; s < n_steps; ++s) NB_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
-    }
+    if ((rc = run_steps(c, n_steps)) != NB_OK) return rc;
     if (c->sp.world > 1) NB_CUDA(c, cudaStreamSynchronize(c->stream));
     return NB_OK;
 }
@@ -401,13 +465,7 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
     if (ms_force) *ms_force = 0.f;
     if (!ms_force) {            // whole region only: keep the graph path
         NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-        if (c->par.flags & NB_FLAG_NO_GRAPH) {
-            for (int s = 0; s < n_steps; ++s)
-                if ((rc = enqueue_step(c, nullptr, nullptr)) != NB_OK) return rc;
-        } else {
-            if ((rc = ensure_graph(c)) != NB_OK) return rc;
-            for (int s = 0; s < n_steps; ++s) NB_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
-        }
+        if ((rc = run_steps(c, n_steps)) != NB_OK) return rc;
         NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
         NB_CUDA(c, cudaEventSynchronize(c->ev1));
         if (ms_total) NB_CUDA(c, cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
@@ -420,7 +478,7 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
     }
     NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int s = 0; s < n_steps; ++s)
-        if ((rc = enqueue_step(c, c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
+        if ((rc = enqueue_step(c, c->sp, c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
     NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     NB_CUDA(c, cudaEventSynchronize(c->ev1));
     if (ms_total) NB_CUDA(c, cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
@@ -446,7 +504,7 @@ int nb_step_profile(nb_ctx *c, int n_steps, float ms[4])
     }
     for (int k = 0; k < 4; ++k) ms[k] = 0.f;
     for (int s = 0; s < n_steps; ++s) {
-        if ((rc = enqueue_step(c, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
+        if ((rc = enqueue_step(c, c->sp, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
         NB_CUDA(c, cudaEventSynchronize(c->fev[4]));
         for (int k = 0; k < 4; ++k) {
             float t = 0.f;
@@ -470,6 +528,7 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->candidates = (int64_t)ctr.candidates;
     out->exact_chunks = (int64_t)ctr.exact_chunks;
     out->fast_chunks = (int64_t)ctr.fast_chunks;
+    out->culled_parts = (int64_t)ctr.culled_parts;
     out->n = d.n;
     out->overflow = ctr.overflow_flag;
     out->events_dropped = ctr.ev_dropped;
@@ -588,6 +647,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.rank = params->world > 1 ? params->rank : 0;
     sp.force_grid = force_grid;
     sp.lg_parts_override = -1;
+    sp.sort_min_n = 0;
     StepDesc d;
     plan_host(&d, &sp, n);
     out->n = d.n;

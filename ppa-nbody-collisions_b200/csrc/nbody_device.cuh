@@ -27,6 +27,8 @@ constexpr int kTJ = 512;                     // j bodies per shared-memory tile
 constexpr int kMaxLgParts = 3;               // smallest work unit = kTJ >> 3 = 64 bodies
 constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
 constexpr int kTileBytes = kTileFloats * 4;
+constexpr int kSubPart = 64;                 // bodies per bounding box of the sorted j stream (= the smallest part)
+constexpr int kSortedTileFloats = 5 * kTJ + 4 * (kTJ / kSubPart);   // x, y, m, r, orig planes + 8 float4 boxes
 constexpr int kSC = 32;                      // j bodies per sub-chunk (granularity of the collision pre-test)
 constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
@@ -49,6 +51,7 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int n_jtiles;                 // T = ceil(n / kTJ)
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
     int lg_parts;                 // a work unit is kTJ >> lg_parts bodies of one j-tile (0 .. kMaxLgParts)
+    int sorted;                   // 1: the force kernel streams the cell-sorted j-tiles (jts) this step
     long long units;              // U = n_iblocks * T << lg_parts  (work units of this rank)
     float rmax;                   // max radius over live bodies
     unsigned step;                // steps since upload
@@ -64,6 +67,7 @@ struct Counters {
     unsigned long long candidates;
     unsigned long long exact_chunks;
     unsigned long long fast_chunks;
+    unsigned long long culled_parts;   // parts that ran without the pre-test (sorted stream)
     unsigned long long steps;
     unsigned cand_count;          // entries pushed to the candidate list this step
     int overflow_flag;            // sticky
@@ -84,12 +88,19 @@ struct StepParams {
     int force_grid;
     int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
     int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
+    int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
 };
 
 struct DevState {
     float4 *pm;
     float2 *vel;
     float *jt;
+    float *jts;                   // cell-sorted j-tiles (kSortedTileFloats each), rebuilt every step when desc->sorted
+    unsigned *skey[2];            // radix sort ping-pong: Morton cell keys
+    int *sidx[2];                 //                       body indices (sidx[0][slot] = body after the sort)
+    int *sinv;                    // body -> slot
+    int *host_n;                  // device pointer to a pinned host int: the live body count after every step
+    unsigned *shist;              // 256 x radix blocks
     unsigned char *post;          // world chunks of shard_cap * 24 B
     float2 *fpart;
     int *head;
@@ -118,7 +129,9 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
-cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s);
+cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_count, cudaStream_t s);
+cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
+size_t sort_hist_entries(int cap);
 cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s);
 cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s);
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,

@@ -106,6 +106,7 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.lg_parts = whole < 16 * grid ? 3 : (whole < 100 * grid ? 2 : (whole < 400 * grid ? 1 : 0));
     if (p.lg_parts_override >= 0) d.lg_parts = p.lg_parts_override;
     d.units = whole << d.lg_parts;
+    d.sorted = (p.sort_min_n > 0 && p.coverage == NB_COVERAGE_FULL && n >= p.sort_min_n && n >= 2 * kTJ) ? 1 : 0;
     d.rmax = rmax;
     d.step = step;
 }
@@ -120,6 +121,8 @@ __global__ void plan_kernel(DevState st, StepParams p, int n)
     st.res->ticket = 0u;
     Counters c = {};
     *st.ctr = c;
+    *st.host_n = n;
+    __threadfence_system();
 }
 
 // owner(u): the force CTA whose unit range [c U / G, (c+1) U / G) holds unit u
@@ -160,7 +163,7 @@ struct Window {            // the j ranges a group never visits: [a0,b0) u [a1,b
     int a0, b0, a1, b1;
 };
 
-template <bool PACKED>
+template <bool PACKED, bool TEST = true>
 __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const float2 ms, const float2 nxi,
                                       const float2 nyi, const float thr, float2 &fx, float2 &fy, bool &cand)
 {
@@ -168,8 +171,10 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
         const float2 dx = __fadd2_rn(xs, nxi);
         const float2 dy = __fadd2_rn(ys, nyi);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-        cand |= (d2.x <= thr);
-        cand |= (d2.y <= thr);
+        if (TEST) {
+            cand |= (d2.x <= thr);
+            cand |= (d2.y <= thr);
+        }
         const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
         const float2 s = __fmul2_rn(__fmul2_rn(inv, inv), __fmul2_rn(inv, ms));
         fx = __ffma2_rn(dx, s, fx);
@@ -178,8 +183,10 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
         const float dx0 = xs.x + nxi.x, dy0 = ys.x + nyi.x;
         const float dx1 = xs.y + nxi.y, dy1 = ys.y + nyi.y;
         const float d20 = fmaf(dx0, dx0, dy0 * dy0), d21 = fmaf(dx1, dx1, dy1 * dy1);
-        cand |= (d20 <= thr);
-        cand |= (d21 <= thr);
+        if (TEST) {
+            cand |= (d20 <= thr);
+            cand |= (d21 <= thr);
+        }
         const float i0 = rsqrt_approx(d20), i1 = rsqrt_approx(d21);
         const float s0 = (i0 * i0) * (i0 * ms.x), s1 = (i1 * i1) * (i1 * ms.y);
         fx.x = fmaf(dx0, s0, fx.x);
@@ -196,7 +203,8 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
 // atomicAdd (warp-aggregated), then threaded into the row's chain.
 __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px, const int j0, const float xi,
                                             const float yi, const float ri, const bool active, const int row,
-                                            const int excl, const Window &w, float2 &ax, float2 &ay, const int lane)
+                                            const int excl, const Window &w, float2 &ax, float2 &ay, const int lane,
+                                            const bool sorted)
 {
     unsigned hits = 0;
 #pragma unroll 2
@@ -207,9 +215,10 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
         const float rs = ri + rj;
         const float rs2 = rs * rs;
         const bool hit = d2 <= rs2;
-        const int j = j0 + jj;
+        // sorted j stream: the body's original index rides in the fifth plane (-1 for padding)
+        const int j = sorted ? __float_as_int(px[4 * kTJ + jj]) : j0 + jj;
         const bool in_excl = ((j >= w.a0) & (j < w.b0)) | ((j >= w.a1) & (j < w.b1));
-        const bool valid = active & (j != excl) & !in_excl;
+        const bool valid = active & (j >= 0) & (j != excl) & !in_excl;
         const float inv = rsqrt_approx(d2);
         const float s = (inv * inv) * (inv * mj);
         if (valid && !hit) {                      // even j -> .x, odd j -> .y: the fast path's lane assignment
@@ -236,7 +245,7 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
             const unsigned idx = base + __popc(pending & ((1u << lane) - 1u));
             if (idx < (unsigned)st.cand_cap) {
                 const int prev = atomicExch(&st.head[row], (int)idx);
-                st.cand[idx] = make_int2(j0 + jj, prev);
+                st.cand[idx] = make_int2(sorted ? __float_as_int(px[4 * kTJ + jj]) : j0 + jj, prev);
             } else {
                 st.ctr->overflow_flag = 1;
             }
@@ -251,14 +260,14 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
 // ring stage: its bodies arrive by 1-D TMA bulk copies completing on an mbarrier, the last warp to finish a
 // stage refills it with the segment kStages ahead.  Inside a segment every part is a checkpoint: its sums are
 // kept only if the row's collision pre-test stayed clear over the part, otherwise the part is redone exactly.
-template <bool PACKED, int WARPS, int IPT, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState st, const StepParams p)
+template <bool PACKED, int WARPS, int IPT, bool SORTED>
+__device__ __forceinline__ void force_body(const DevState &st, const StepParams &p, float *tiles_dyn)
 {
     static_assert(WARPS * 32 * IPT == kIBlock, "one CTA covers one i-block");
     static_assert(IPT << kMaxLgParts <= 32, "one redo bit per (part, row) of a segment");
     constexpr int THREADS = WARPS * 32;
     constexpr int WROWS = 32 * IPT;               // rows per warp (a divisor of the 128-row visit-order group)
-    __shared__ __align__(128) float tiles[kStages][kTileFloats];
+    float(*tiles)[kSortedTileFloats] = reinterpret_cast<float(*)[kSortedTileFloats]>(tiles_dyn);   // kStages of the larger layout
     __shared__ __align__(8) unsigned long long full_bar[kStages];
     __shared__ unsigned done_cnt[kStages];      // warps that finished the segment in each stage (refill trigger)
     // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per segment with a
@@ -282,6 +291,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
     const bool fexact = st.desc->force_exact != 0;
     const float rmax = st.desc->rmax;
     const int jw = kTJ >> lgP;                    // bodies per part
+    constexpr bool sorted = SORTED;               // cell-sorted order: 5 planes + bounding boxes per tile, rows are slots
+    const float *jsrc = sorted ? st.jts : st.jt;
+    const int tile_floats = sorted ? kSortedTileFloats : kTileFloats;
     const int nsc = jw / kSC;                     // 32-body sub-chunks per part
 
     int ib = (int)(u0 / TP);
@@ -294,15 +306,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
 
     auto issue = [&](int stage, int vv, int parts) {   // one thread at a time
         const int tile = vv >> lgP, part = vv & (P - 1);
-        const float *src = st.jt + (size_t)tile * kTileFloats + part * jw;
+        const float *src = jsrc + (size_t)tile * tile_floats + part * jw;
         float *dst = tiles[stage] + part * jw;
         const unsigned plane_bytes = (unsigned)(parts * jw) * 4u;
-        mbar_expect_tx(&full_bar[stage], 4u * plane_bytes);
-        if (parts == P && lgP == 0) {
-            bulk_g2s(dst, src, kTileBytes, &full_bar[stage]);
-        } else {
+        const unsigned box_bytes = (unsigned)(parts * jw / kSubPart) * 16u;
+        if (parts == P) {                              // the whole tile is contiguous in either layout
+            mbar_expect_tx(&full_bar[stage], (unsigned)tile_floats * 4u);
+            bulk_g2s(tiles[stage], jsrc + (size_t)tile * tile_floats, (unsigned)tile_floats * 4u, &full_bar[stage]);
+        } else if (!sorted) {
+            mbar_expect_tx(&full_bar[stage], 4u * plane_bytes);
 #pragma unroll
             for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + pl * kTJ, src + pl * kTJ, plane_bytes, &full_bar[stage]);
+        } else {
+            mbar_expect_tx(&full_bar[stage], 5u * plane_bytes + box_bytes);
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) bulk_g2s(dst + pl * kTJ, src + pl * kTJ, plane_bytes, &full_bar[stage]);
+            const int box0 = 5 * kTJ + 4 * (part * jw / kSubPart);
+            bulk_g2s(tiles[stage] + box0, jsrc + (size_t)tile * tile_floats + box0, box_bytes, &full_bar[stage]);
         }
     };
     auto advance = [&](int &vv, int &rem) {            // step a cursor over one segment
@@ -332,7 +352,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
     Window w = {0, 0, 0, 0};
     int wbase = 0, gbase = 0;
     bool warp_active = false;
-    unsigned n_fast = 0, n_exact = 0;
+    unsigned n_fast = 0, n_exact = 0, n_culled = 0;
 
     for (int it = 0; left > 0; ++it) {
         if (it == 0 || v == 0) {
@@ -345,7 +365,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                 const int i = wbase + 32 * q + lane;
                 const bool act = i < row_act_hi;
                 float4 b = make_float4(kDummyCoord, kDummyCoord, 0.f, 0.f);
-                if (act) b = st.pm[i];
+                if (act) {
+                    if (sorted) {                 // rows are slots of the sorted order: the body sits in the sorted tiles
+                        const float *t = st.jts + (size_t)(i / kTJ) * kSortedTileFloats + (i & (kTJ - 1));
+                        b = make_float4(t[0], t[kTJ], 0.f, t[3 * kTJ]);
+                    } else {
+                        b = st.pm[i];
+                    }
+                }
                 nxi[q] = make_float2(-b.x, -b.x);
                 nyi[q] = make_float2(-b.y, -b.y);
                 const float rs = b.w + rmax;
@@ -385,18 +412,55 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                     tfy[q] = make_float2(0.f, 0.f);
                     cand[q] = pspecial;
                 }
-#pragma unroll 8
-                for (int k4 = 0; k4 < jw / 4; ++k4) {
-                    const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
-                    const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
-                    const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
+                // Sorted stream: the part's bodies are close together.  If no row of this warp lies inside their
+                // bounding box inflated by the row's pre-test radius, no pair of the part can pass the pre-test
+                // (|dx| or |dy| alone already exceeds the radius) and the loop runs without it.
+                bool may_hit = true;
+                if (sorted && !pspecial) {
+                    const float4 *boxes = reinterpret_cast<const float4 *>(tiles[stage] + 5 * kTJ) + (part0 + pp) * (jw / kSubPart);
+                    float4 bb = boxes[0];
+                    for (int k = 1; k < jw / kSubPart; ++k) {
+                        const float4 o = boxes[k];
+                        bb = make_float4(fminf(bb.x, o.x), fminf(bb.y, o.y), fmaxf(bb.z, o.z), fmaxf(bb.w, o.w));
+                    }
+                    bool inside = false;
 #pragma unroll
                     for (int q = 0; q < IPT; ++q) {
-                        pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
-                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
-                        pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
-                                      nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                        const float R = sqrtf(thr[q]) * 1.0002f;        // thr < 0 (inactive row): NaN, never inside
+                        const float x = -nxi[q].x, y = -nyi[q].x;
+                        inside |= (x >= bb.x - R) & (x <= bb.z + R) & (y >= bb.y - R) & (y <= bb.w + R);
                     }
+                    may_hit = __any_sync(0xffffffffu, inside);
+                }
+                if (may_hit) {
+#pragma unroll 8
+                    for (int k4 = 0; k4 < jw / 4; ++k4) {
+                        const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
+                        const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
+                        const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
+#pragma unroll
+                        for (int q = 0; q < IPT; ++q) {
+                            pair2<PACKED, true>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
+                                                nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                            pair2<PACKED, true>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
+                                                nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                        }
+                    }
+                } else {
+#pragma unroll 8
+                    for (int k4 = 0; k4 < jw / 4; ++k4) {
+                        const float4 X = *reinterpret_cast<const float4 *>(tl + 4 * k4);
+                        const float4 Y = *reinterpret_cast<const float4 *>(tl + kTJ + 4 * k4);
+                        const float4 M = *reinterpret_cast<const float4 *>(tl + 2 * kTJ + 4 * k4);
+#pragma unroll
+                        for (int q = 0; q < IPT; ++q) {
+                            pair2<PACKED, false>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
+                                                 nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                            pair2<PACKED, false>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
+                                                 nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                        }
+                    }
+                    ++n_culled;
                 }
                 unsigned bits = 0;
 #pragma unroll
@@ -432,9 +496,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                         ay = fy[k];
                         th = thr[k];
                     }
-                const int row = wbase + 32 * q + lane;
-                const int t = row - gbase;
-                const bool act = mine && row < row_act_hi;
+                const int slot = wbase + 32 * q + lane;
+                const int t = slot - gbase;
+                const bool act = mine && slot < row_act_hi;
+                // the row's ORIGINAL index: what candidates, the self test and the window refer to
+                const int row = (sorted && act) ? st.sidx[0][slot] : slot;
                 int excl = row;
                 if (limit_first != kGroup) excl = limit_first > 0 ? gbase + (t % limit_first) : -1;
                 const float xi = -nx.x, yi = -ny.x;
@@ -458,7 +524,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
                     const bool need = mine && cc;
                     if (__any_sync(0xffffffffu, need)) {
                         ++n_exact;
-                        exact_chunk(st, px, j0, xi, yi, ri, act && need, row, excl, w, ax, ay, lane);
+                        exact_chunk(st, px, j0, xi, yi, ri, act && need, row, excl, w, ax, ay, lane, sorted);
                     }
                     if (mine && !cc) {
                         ax = __fadd2_rn(ax, tx);
@@ -519,21 +585,38 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
     if (p.count_stats && lane == 0) {
         atomicAdd(&st.ctr->fast_chunks, (unsigned long long)n_fast);
         atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_exact);
+        atomicAdd(&st.ctr->culled_parts, (unsigned long long)n_culled);
     }
+}
+
+// The step's descriptor decides (on the device) whether this step runs on the cell-sorted order; both bodies are
+// instantiated so that neither pays for the other's code in its hot loop.
+template <bool PACKED, int WARPS, int IPT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState st, const StepParams p)
+{
+    extern __shared__ __align__(128) float tiles_dyn[];
+    if (st.desc->sorted)
+        force_body<PACKED, WARPS, IPT, true>(st, p, tiles_dyn);
+    else
+        force_body<PACKED, WARPS, IPT, false>(st, p, tiles_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------
 // finish: per-row epilogue of ComputeForces + MoveBodies
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool finish_row(const DevState &st, const StepParams &p, const StepDesc &d, const int row)
+// `slot` is the thread's position in this rank's range [row_lo, row_hi): the body's index itself, or -- when
+// the step ran on the cell-sorted order -- its slot in that order (partial sums and post rows are by slot,
+// everything else by the body's original index).
+__device__ __forceinline__ bool finish_row(const DevState &st, const StepParams &p, const StepDesc &d, const int slot)
 {
-    if (row >= d.row_hi) return false;
-    const int local = row - d.row_lo;
+    if (slot >= d.row_hi) return false;
+    const int local = slot - d.row_lo;
+    const int row = d.sorted ? st.sidx[0][slot] : slot;
     float4 *out_pm = post_pm(st, p.world > 1 ? p.rank : 0);
     float2 *out_vel = post_vel(st, p.world > 1 ? p.rank : 0);
     const float4 b = st.pm[row];
     float2 v = st.vel[row];
-    if (row >= d.row_act_hi) {                    // frozen tail: no thread in either reference kernel
+    if (slot >= d.row_act_hi) {                   // frozen tail: no thread in either reference kernel
         out_pm[local] = b;
         out_vel[local] = v;
         return b.z != 0.f;
@@ -616,7 +699,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     const StepDesc &d = *st.desc;
     const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     const bool survives = finish_row(st, p, d, row);
-    if (p.world <= 1) {
+    if (p.world <= 1 && !d.sorted) {
         // single GPU: the survivor count of the compaction tiles is taken here (saves the count kernel);
         // tile_count is zero on entry (upload / the previous scatter clear it)
         const unsigned m = __ballot_sync(0xffffffffu, survives);
@@ -627,20 +710,23 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
 // ------------------------------------------------------------------------------------------------
 // compaction: count, then scatter (+ plan of the next step in the last CTA)
 // ------------------------------------------------------------------------------------------------
+// post rows are stored by slot (= index, or position in the sorted order), rank chunk by rank chunk
+__device__ __forceinline__ int post_slot(const DevState &st, int i) { return st.desc->sorted ? st.sinv[i] : i; }
 __device__ __forceinline__ float4 load_post_pm(const DevState &st, int rpr, int i)
 {
-    const int rk = i / rpr, loc = i - rk * rpr;
+    const int s = post_slot(st, i), rk = s / rpr, loc = s - rk * rpr;
     return post_pm(st, rk)[loc];
 }
 __device__ __forceinline__ float2 load_post_vel(const DevState &st, int rpr, int i)
 {
-    const int rk = i / rpr, loc = i - rk * rpr;
+    const int s = post_slot(st, i), rk = s / rpr, loc = s - rk * rpr;
     return post_vel(st, rk)[loc];
 }
 
-__global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st)
+__global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st, const StepParams p)
 {
     __shared__ int s_cnt[kCompactThreads / 32];
+    if (p.world <= 1 && !st.desc->sorted) return;      // finish_kernel already counted
     const int n = st.desc->n, rpr = st.desc->rows_per_rank;
     const int base = blockIdx.x * kCompactTile;
     if (base >= n) return;
@@ -765,6 +851,8 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
         *st.desc = d;
         st.res->rmax_bits = 0u;
         st.res->ticket = 0u;
+        *st.host_n = n_new;                       // the host picks the next steps' graph by this (pinned, mapped)
+        __threadfence_system();
     }
 }
 
@@ -837,6 +925,8 @@ __global__ void __launch_bounds__(128) render_kernel(const DevState st, const in
 //   2: packed,       4 warps x 4 rows/lane, <= 128 registers (4 CTAs = 16 warps per SM)
 //   3: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
 //   4: scalar FP32,  4 warps x 4 rows/lane (A/B reference for the packed path)
+constexpr int kForceDynSmem = kStages * kSortedTileFloats * 4;
+
 #define NB_FORCE_VARIANTS(X)     \
     X(0, true, 8, 2, 3)          \
     X(1, true, 8, 2, 4)          \
@@ -858,9 +948,9 @@ cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStre
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s)
 {
     switch (variant) {
-#define X(ID, PK, W, I, MB)                                                        \
-    case ID:                                                                       \
-        force_kernel<PK, W, I, MB><<<p.force_grid, W * 32, 0, s>>>(st, p);         \
+#define X(ID, PK, W, I, MB)                                                                    \
+    case ID:                                                                                   \
+        force_kernel<PK, W, I, MB><<<p.force_grid, W * 32, kForceDynSmem, s>>>(st, p);         \
         break;
         NB_FORCE_VARIANTS(X)
 #undef X
@@ -877,11 +967,11 @@ cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_compact(const DevState &st, const StepParams &p, cudaStream_t s)
+cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_count, cudaStream_t s)
 {
     const int grid = (st.cap + kCompactTile - 1) / kCompactTile;
-    if (p.world > 1) {            // the other ranks' rows were counted on their GPUs: recount everything here
-        count_kernel<<<grid, kCompactThreads, 0, s>>>(st);
+    if (p.world > 1 || always_count) {       // rows counted on other GPUs, or by slot instead of by index: recount
+        count_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -920,7 +1010,8 @@ int force_occupancy(int variant, int *regs, int *threads)
 #define X(ID, PK, W, I, MB)                                                                        \
     case ID:                                                                                       \
         thr = W * 32;                                                                              \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<PK, W, I, MB>, thr, 0);   \
+        cudaFuncSetAttribute(force_kernel<PK, W, I, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kForceDynSmem); \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<PK, W, I, MB>, thr, kForceDynSmem);   \
         cudaFuncGetAttributes(&fa, force_kernel<PK, W, I, MB>);                                    \
         break;
         NB_FORCE_VARIANTS(X)

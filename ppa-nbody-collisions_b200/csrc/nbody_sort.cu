@@ -1,0 +1,196 @@
+// nbody_sort.cu -- the cell-sorted shadow copy of the j stream (full coverage, large n).
+//
+// The force kernel's per-pair collision pre-test costs one issue slot in thirteen.  It can be skipped for a
+// (warp rows, j part) pair when no row of the warp lies inside the part's bounding box inflated by the row's
+// pre-test radius -- which only happens often if the bodies of a part are close together.  So, after every
+// compaction, the bodies are sorted by a 16-bit Morton cell key (stable LSD radix sort, two 8-bit passes:
+// deterministic, ties keep index order) and a second set of j-tiles is built in that order:
+//   jts[tile] = { x[512] y[512] m[512] r[512] orig[512] bbox[8] }       (bbox: float4 per 64 bodies)
+// The canonical arrays (pm, vel, jt) and everything that depends on body order -- rows, visit order,
+// candidates (carried by ORIGINAL index), compaction, sharding -- are untouched.
+#include "nbody_device.cuh"
+
+namespace nb {
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortPerBlock = 2048;             // elements per radix block: 8 warps x 256 contiguous elements
+constexpr int kSortPerWarp = kSortPerBlock / (kSortThreads / 32);
+
+__device__ __forceinline__ unsigned spread8(unsigned v)      // abcdefgh -> 0a0b0c0d0e0f0g0h
+{
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) keys_kernel(const DevState st, const StepParams p)
+{
+    if (!st.desc->sorted) return;
+    const int n = st.desc->n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = st.pm[i];
+    // 256 x 256 cells over the field [-W, W] x [-H, H]; bodies outside are clamped to the border cells
+    const float sx = 128.0f / (float)p.field_w, sy = 128.0f / (float)p.field_h;
+    int cx = (int)((b.x + (float)p.field_w) * sx), cy = (int)((b.y + (float)p.field_h) * sy);
+    cx = cx < 0 ? 0 : (cx > 255 ? 255 : cx);
+    cy = cy < 0 ? 0 : (cy > 255 ? 255 : cy);
+    st.skey[0][i] = spread8((unsigned)cx) | (spread8((unsigned)cy) << 1);
+    st.sidx[0][i] = i;
+}
+
+// histogram of one 8-bit digit per radix block: hist[bin * nblocks + block]
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const DevState st, const int src, const int shift)
+{
+    __shared__ unsigned s_hist[256];
+    if (!st.desc->sorted) return;
+    const int n = st.desc->n;
+    const int nblocks = gridDim.x;
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kSortPerBlock;
+    for (int k = threadIdx.x; k < kSortPerBlock; k += kSortThreads) {
+        const int i = base + k;
+        if (i < n) atomicAdd(&s_hist[(st.skey[src][i] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    st.shist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// exclusive scan of the 256 * nblocks table, in place (one block)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(const DevState st, const int nblocks)
+{
+    __shared__ unsigned s_part[1024];
+    if (!st.desc->sorted) return;
+    const int m = 256 * nblocks;
+    const int per = (m + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, m);
+    unsigned sum = 0;
+    for (int k = lo; k < hi; ++k) sum += st.shist[k];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {               // Hillis-Steele inclusive scan of the partials
+        const unsigned v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = s_part[threadIdx.x] - sum;
+    for (int k = lo; k < hi; ++k) {
+        const unsigned v = st.shist[k];
+        st.shist[k] = run;
+        run += v;
+    }
+}
+
+// stable scatter of one digit: every warp walks its 512 contiguous elements in order
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevState st, const int src, const int shift)
+{
+    __shared__ unsigned s_cnt[kSortThreads / 32][256];        // per warp: digit counts, then running offsets
+    if (!st.desc->sorted) return;
+    const int n = st.desc->n;
+    const int nblocks = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dst = src ^ 1;
+    for (int k = threadIdx.x; k < (kSortThreads / 32) * 256; k += kSortThreads) (&s_cnt[0][0])[k] = 0;
+    __syncthreads();
+    const int wbase = blockIdx.x * kSortPerBlock + warp * kSortPerWarp;
+    for (int k = lane; k < kSortPerWarp; k += 32) {
+        const int i = wbase + k;
+        if (i < n) atomicAdd(&s_cnt[warp][(st.skey[src][i] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    {   // thread b: turn the per-warp counts of bin b into output offsets (global base + earlier warps)
+        const int b = threadIdx.x;
+        unsigned run = st.shist[(size_t)b * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w) {
+            const unsigned c = s_cnt[w][b];
+            s_cnt[w][b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int k = lane; k < kSortPerWarp; k += 32) {           // warp-uniform trip count
+        const int i = wbase + k;
+        const bool valid = i < n;
+        const unsigned key = valid ? st.skey[src][i] : 0u;
+        const unsigned digit = valid ? (key >> shift) & 0xffu : 0x100u + lane;      // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned pos = 0;
+        if (valid) pos = s_cnt[warp][digit] + rank;
+        __syncwarp();
+        if (valid && rank == __popc(peers) - 1) s_cnt[warp][digit] += (unsigned)__popc(peers);   // last peer advances
+        __syncwarp();
+        if (valid) {
+            st.skey[dst][pos] = key;
+            st.sidx[dst][pos] = st.sidx[src][i];
+        }
+    }
+}
+
+// sorted j-tiles + bounding boxes; slot s of the sorted order holds body sidx[0][s]
+__global__ void __launch_bounds__(256) gather_kernel(const DevState st)
+{
+    __shared__ float4 s_box[8];
+    if (!st.desc->sorted) return;
+    const int n = st.desc->n;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pad_end = (n + kTJ - 1) / kTJ * kTJ;
+    if (blockIdx.x * blockDim.x >= pad_end) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 b = make_float4(kPadCoord, kPadCoord, 0.f, 0.f);
+    int orig = -1;
+    if (s < n) {
+        orig = st.sidx[0][s];
+        b = st.pm[orig];
+        st.sinv[orig] = s;
+    }
+    float *t = st.jts + (size_t)(s / kTJ) * kSortedTileFloats + (s & (kTJ - 1));
+    t[0] = b.x;
+    t[kTJ] = b.y;
+    t[2 * kTJ] = b.z;
+    t[3 * kTJ] = b.w;
+    t[4 * kTJ] = __int_as_float(orig);
+    // bounding box per 64 slots; pads do not count (an empty box overlaps nothing)
+    const float inf = __int_as_float(0x7f800000);
+    float x0 = s < n ? b.x : inf, y0 = s < n ? b.y : inf, x1 = s < n ? b.x : -inf, y1 = s < n ? b.y : -inf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) s_box[warp] = make_float4(x0, y0, x1, y1);
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const float4 a = s_box[2 * threadIdx.x], c = s_box[2 * threadIdx.x + 1];
+        const int sub = (blockIdx.x * blockDim.x) / kSubPart + threadIdx.x;      // 64-slot sub-part index
+        float4 *box = reinterpret_cast<float4 *>(st.jts + (size_t)(sub / (kTJ / kSubPart)) * kSortedTileFloats + 5 * kTJ) +
+                      (sub % (kTJ / kSubPart));
+        *box = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fmaxf(a.z, c.z), fmaxf(a.w, c.w));
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s)
+{
+    const int nblocks = (st.cap + kSortPerBlock - 1) / kSortPerBlock;
+    keys_kernel<<<(st.cap + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s>>>(st, p);
+    for (int pass = 0; pass < 2; ++pass) {
+        radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass);
+        radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass);
+    }
+    gather_kernel<<<(st.cap + kTJ + 255) / 256, 256, 0, s>>>(st);
+    return cudaGetLastError();
+}
+
+size_t sort_hist_entries(int cap) { return (size_t)256 * ((cap + kSortPerBlock - 1) / kSortPerBlock); }
+
+}  // namespace nb

@@ -29,7 +29,7 @@ def _gpu_count() -> int:
         return 0
 
 
-def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int, steps: int, out_dir: str):
+def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int, steps: int, out_dir: str, sort_min_n: int = 0):
     sys.path.insert(0, str(ROOT))
     import torch
     import torch.distributed as dist
@@ -43,7 +43,7 @@ def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int
     dist.broadcast_object_list(ids, src=0)
     block0 = nb.generate(nb.SCENARIO_SQUARE, n0, field_w=field, field_h=field)
     sim = nb.Simulation(n0, field_w=field, field_h=field, coverage=coverage, device=rank, rank=rank, world=world,
-                        event_capacity=64 * n0)
+                        event_capacity=64 * n0, sort_min_n=sort_min_n)
     sim.comm_init(ids[0])
     sim.upload(block0, n0)
     states = []
@@ -60,11 +60,12 @@ def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("n0,field,coverage", [(16384, 100000, 0), (16384, 100000, 1), (3000, 12000, 1), (700, 3000, 0)])
-def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage):
+@pytest.mark.parametrize("n0,field,coverage,sort_min_n", [(16384, 100000, 0, 0), (16384, 100000, 1, 0), (3000, 12000, 1, 0),
+                                                         (700, 3000, 0, 0), (16384, 100000, 1, 1024), (3000, 12000, 1, 2900)])
+def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage, sort_min_n):
     import torch.multiprocessing as mp
     world, steps = 2, 4
-    mp.spawn(_worker, args=(world, _free_port(), n0, field, coverage, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n0, field, coverage, steps, str(tmp_path), sort_min_n), nprocs=world, join=True)
     block = nb.generate(nb.SCENARIO_SQUARE, n0, field_w=field, field_h=field)
     par = oracle.params(field_w=field, field_h=field, coverage=coverage)
     n = n0

@@ -53,9 +53,10 @@ def _compare_events(ev, ev_cpu, tag):
     assert np.array_equal(ev["kind"], ev_cpu["kind"]), f"{tag}: event kinds"
 
 
-def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=0.1, trace=None, flags=0, resync=False):
+def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=0.1, trace=None, flags=0, resync=False,
+                      sort_min_n=0):
     sim = nb.Simulation(n0, dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage,
-                        event_capacity=max(64 * n0, 4096), flags=flags)
+                        event_capacity=max(64 * n0, 4096), flags=flags, sort_min_n=sort_min_n)
     try:
         sim.upload(block0, n0)
         cpu = block0.copy()
@@ -398,3 +399,18 @@ def test_driver_checkpoint_resume(nb, tmp_path):
     r = run("--steps", "4", "--resume", "half.bin", "--dump-state", "resumed.bin")
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "resumed.bin").read_bytes() == (tmp_path / "full.bin").read_bytes()
+
+
+@pytest.mark.parametrize("n,field,sort_min_n,steps", [(1500, 6000, 1024, 6), (3000, 12000, 2900, 6), (16384, 100000, 1024, 10),
+                                                      (20000, 60000, 19000, 8)])
+def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
+    """The cell-sorted shadow order (default from 98 304 bodies on) forced on at small n: same events, survivors,
+    masses and radii as the oracle; the second and fourth case cross the threshold while running, so steps on the
+    sorted order and on the bodies' own order follow each other in both graphs."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n)
+    assert st["culled_parts"] > 0, "the sorted order never skipped a pre-test"
+    st = _run_side_by_side(nb, oracle, block0, n, 3, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n, flags=nb.FLAG_NO_GRAPH)
+    assert st["culled_parts"] > 0
+    st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n, flags=nb.FLAG_NO_SORT)
+    assert st["culled_parts"] == 0
