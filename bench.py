@@ -349,17 +349,20 @@ def main() -> int:
                          "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_force_1m_ncu.json); algorithmic HBM bytes of "
                                          "the launch are 32 n (one pass over the 16 B/body i rows and j tiles): the kernel is "
                                          "FP32-issue bound, not HBM bound",
-                         "kernel": "force_kernel<packed f32x2>", "ms_per_launch": ms_force_max / args.steps,
+                         "kernel": "force_kernel<packed f32x2, 8 warps x 2 rows/lane>", "ms_per_launch": ms_force_max / args.steps,
                          "flop_per_interaction": FLOP_PER_INTERACTION,
                          "peak_source": f"nameplate FP32 FMA: {sms} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz "
                                         f"(MEASURED_PEAKS.json has no FP32 entry; FFMA probe measured 73.9 TFLOP/s, "
                                         f"profiles/r01_fp32_probe.jsonl)",
                          "share_of_step": ms_force_max / ms_total_max},
             "clocks": clocks,
-            "gpu_launches": (3 if world == 1 else 4) * args.steps,
+            # force, finish, scatter (+ count when sharded or sort-capable, + 8 kernels that rebuild the cell-sorted order)
+            "gpu_launches": (3 + (1 if (world > 1 or s1["culled_parts"] > s0["culled_parts"]) else 0)
+                             + (8 if s1["culled_parts"] > s0["culled_parts"] else 0)) * args.steps,
             "wall_s_timed_region": wall,
             "force": {"grid": s1["force_grid"], "regs": s1["force_regs"],
-                      "fast_chunks": s1["fast_chunks"] - s0["fast_chunks"], "exact_chunks": s1["exact_chunks"] - s0["exact_chunks"]},
+                      "fast_chunks": s1["fast_chunks"] - s0["fast_chunks"], "exact_chunks": s1["exact_chunks"] - s0["exact_chunks"],
+                      "parts_without_pretest": s1["culled_parts"] - s0["culled_parts"], "cell_sorted_order": s1["culled_parts"] > s0["culled_parts"]},
             "collision_events": s1["candidates"] - s0["candidates"],
         }
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -373,6 +376,7 @@ def main() -> int:
             "compact": {"ms_per_launch": prof["compact"] / prof_steps, "bytes_per_body": cmp_b,
                         "achieved_gbs": cmp_b * n_mid / (prof["compact"] / prof_steps * 1e-3) / 1e9},
             "allgather_ms": prof["allgather"] / prof_steps,
+            "sort_ms": prof["sort"] / prof_steps,
             "note": "O(n) kernels, < 0.02 % of the step at this n: launch/latency bound rather than bandwidth bound",
         }
         for k in ("finish", "compact"):

@@ -137,8 +137,9 @@ int nb_num_bodies(nb_ctx *ctx, int *n);            /* synchronises */
 int nb_step(nb_ctx *ctx, int n_steps);
 int nb_step_timed(nb_ctx *ctx, int n_steps, float *ms_total, float *ms_force);
 /* Per-kernel device times (ms, summed over n_steps, CUDA events on the context's stream, no graph):
- * ms[0] force, ms[1] finish (bookkeeping + integrate), ms[2] allgather (0 on one GPU), ms[3] compaction. */
-int nb_step_profile(nb_ctx *ctx, int n_steps, float ms[4]);
+ * ms[0] force, ms[1] finish (bookkeeping + integrate), ms[2] allgather (0 on one GPU), ms[3] compaction,
+ * ms[4] rebuild of the cell-sorted order (0 when it is not in use). */
+int nb_step_profile(nb_ctx *ctx, int n_steps, float ms[5]);
 int nb_sync(nb_ctx *ctx);
 int nb_get_stats(nb_ctx *ctx, nb_stats *out);      /* synchronises */
 

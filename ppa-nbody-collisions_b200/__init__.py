@@ -251,9 +251,9 @@ class Simulation:
 
     def step_profile(self, n_steps: int = 1) -> dict:
         """Per-kernel device times in ms summed over n_steps (no graph): force, finish, allgather, compact."""
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         self._check("nb_step_profile", lib().nb_step_profile(self._h, n_steps, ms))
-        return {"force": ms[0], "finish": ms[1], "allgather": ms[2], "compact": ms[3]}
+        return {"force": ms[0], "finish": ms[1], "allgather": ms[2], "compact": ms[3], "sort": ms[4]}
 
     def sync(self):
         self._check("nb_sync", lib().nb_sync(self._h))

@@ -364,7 +364,7 @@ int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
 }
 
 // one step's launches on the context's stream; f0/f1 (optional) bracket the force kernel, marks (optional,
-// 5 events) separate force | finish | allgather | compaction
+// 6 events) separate force | finish | allgather | compaction | sort
 static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEvent_t f1, cudaEvent_t *marks = nullptr)
 {
     if (f0) NB_CUDA(c, cudaEventRecord(f0, c->stream));
@@ -382,8 +382,9 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     // a sort-capable context always runs the count kernel (it exits at once when finish already counted): the
     // step may have run on the sorted order even if THIS graph will not rebuild it
     NB_CUDA(c, launch_compact(c->st, sp, c->sp.sort_min_n > 0, c->stream));
-    if (sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, sp, c->stream));   // shadow order of the next step
     if (marks) NB_CUDA(c, cudaEventRecord(marks[4], c->stream));
+    if (sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, sp, c->stream));   // shadow order of the next step
+    if (marks) NB_CUDA(c, cudaEventRecord(marks[5], c->stream));
     return NB_OK;
 }
 
@@ -492,21 +493,21 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
     return NB_OK;
 }
 
-int nb_step_profile(nb_ctx *c, int n_steps, float ms[4])
+int nb_step_profile(nb_ctx *c, int n_steps, float ms[5])
 {
     int rc = step_precheck(c, n_steps);
     if (rc != NB_OK) return rc;
     if (!ms) return NB_ERR_INVALID;
-    while ((int)c->fev.size() < 5) {
+    while ((int)c->fev.size() < 6) {
         cudaEvent_t e;
         NB_CUDA(c, cudaEventCreate(&e));
         c->fev.push_back(e);
     }
-    for (int k = 0; k < 4; ++k) ms[k] = 0.f;
+    for (int k = 0; k < 5; ++k) ms[k] = 0.f;
     for (int s = 0; s < n_steps; ++s) {
         if ((rc = enqueue_step(c, c->sp, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
-        NB_CUDA(c, cudaEventSynchronize(c->fev[4]));
-        for (int k = 0; k < 4; ++k) {
+        NB_CUDA(c, cudaEventSynchronize(c->fev[5]));
+        for (int k = 0; k < 5; ++k) {
             float t = 0.f;
             NB_CUDA(c, cudaEventElapsedTime(&t, c->fev[k], c->fev[k + 1]));
             ms[k] += t;

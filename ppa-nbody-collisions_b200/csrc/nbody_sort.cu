@@ -6,8 +6,11 @@
 // compaction, the bodies are sorted by a 16-bit Morton cell key (stable LSD radix sort, two 8-bit passes:
 // deterministic, ties keep index order) and a second set of j-tiles is built in that order:
 //   jts[tile] = { x[512] y[512] m[512] r[512] orig[512] bbox[8] }       (bbox: float4 per 64 bodies)
-// The canonical arrays (pm, vel, jt) and everything that depends on body order -- rows, visit order,
-// candidates (carried by ORIGINAL index), compaction, sharding -- are untouched.
+// A step that runs on this order takes BOTH sides from it: a warp's rows are 64 consecutive slots (so they are
+// close together as well, and their own self pairs sit in one part), partial force sums and post-step rows are
+// stored by slot (sinv maps a body to its slot for the finish / compaction kernels).  Everything that the
+// reference defines by body index -- visit order, candidates, events, survivors' order -- keeps using the
+// original index, which rides along in the fifth plane.
 #include "nbody_device.cuh"
 
 namespace nb {
@@ -59,29 +62,44 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const DevState
     st.shist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// exclusive scan of the 256 * nblocks table, in place (one block)
+// exclusive scan of the 256 * nblocks table, in place: one block walks it in coalesced chunks of 1024 entries
+// (warp shuffles + one shared array of warp sums per chunk) and carries the running total
 __global__ void __launch_bounds__(1024) radix_scan_kernel(const DevState st, const int nblocks)
 {
-    __shared__ unsigned s_part[1024];
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
     if (!st.desc->sorted) return;
     const int m = 256 * nblocks;
-    const int per = (m + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, m);
-    unsigned sum = 0;
-    for (int k = lo; k < hi; ++k) sum += st.shist[k];
-    s_part[threadIdx.x] = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {               // Hillis-Steele inclusive scan of the partials
-        const unsigned v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+    for (int base = 0; base < m; base += 1024) {
+        const int k = base + threadIdx.x;
+        const unsigned v = k < m ? st.shist[k] : 0u;
+        unsigned inc = v;                                        // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        s_part[threadIdx.x] += v;
+        if (warp == 0) {                                         // exclusive scan of the 32 warp sums
+            const unsigned w = s_warp[lane];
+            unsigned winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;
+        }
         __syncthreads();
-    }
-    unsigned run = s_part[threadIdx.x] - sum;
-    for (int k = lo; k < hi; ++k) {
-        const unsigned v = st.shist[k];
-        st.shist[k] = run;
-        run += v;
+        const unsigned carry = s_carry;
+        if (k < m) st.shist[k] = carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + inc;
+        __syncthreads();
     }
 }
 

@@ -60,5 +60,5 @@ for n in [int(a) for a in sys.argv[1:]] or [131072, 1048576]:
                           "frac_roofline_force": pairs * 20 / (frc * 1e-3) / 74.45e12,
                           "frac_roofline_step": pairs * 20 / (tot * 1e-3) / 74.45e12,
                           "culled_parts": s1["culled_parts"] - s0["culled_parts"], "exact": s1["exact_chunks"] - s0["exact_chunks"],
-                          "compact_plus_sort_ms": prof["compact"] / 2}), flush=True)
+                          "compact_ms": prof["compact"] / 2, "sort_ms": prof["sort"] / 2}), flush=True)
         sim.close()
