@@ -183,8 +183,6 @@ int nb_create(nb_ctx **out, const nb_params *params)
     const int world = params->world > 1 ? params->world : 1;
     DevState &st = c->st;
     st.cap = params->n_max;
-    const int iblocks_total = (st.cap + kIBlock - 1) / kIBlock;
-    st.shard_cap = (iblocks_total + world - 1) / world * kIBlock;
     st.cand_cap = params->candidate_capacity > 0 ? params->candidate_capacity
                                                  : (int)std::min<long long>(std::max<long long>(4LL * st.cap, 65536), 1LL << 30);
     st.ev_cap = params->event_capacity > 0 ? params->event_capacity : 0;
@@ -196,7 +194,10 @@ int nb_create(nb_ctx **out, const nb_params *params)
         free_all(c);
         return NB_ERR_INVALID;
     }
-    const int occ = force_occupancy(c->variant, &c->force_regs, &c->force_threads);
+    int iblock = kIBlock;
+    const int occ = force_occupancy(c->variant, &c->force_regs, &c->force_threads, &iblock);
+    const int iblocks_total = (st.cap + iblock - 1) / iblock;
+    st.shard_cap = (iblocks_total + world - 1) / world * iblock;
     if (occ <= 0) {
         set_err(nullptr, "nb_create: force kernel does not fit on an SM");
         free_all(c);
@@ -213,6 +214,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.world = world;
     sp.force_grid = c->sm_count * occ;
     sp.count_stats = 1;
+    sp.iblock = iblock;
     // the cell-sorted order pays for itself from about 1e5 bodies on; it needs all-pairs coverage (the reference's
     // excluded windows are defined by body index) and is sized in only if the capacity can ever reach the threshold
     sp.sort_min_n = 0;
@@ -247,7 +249,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
         NB_ALLOC(st.shist, sizeof(unsigned) * sort_hist_entries(st.cap));
         NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
     }
-    NB_ALLOC(st.fpart, sizeof(float2) * kIBlock * fpart_slabs(sp.force_grid, st.shard_cap));
+    NB_ALLOC(st.fpart, sizeof(float2) * iblock * fpart_slabs(sp.force_grid, st.shard_cap, iblock));
     NB_ALLOC(st.head, sizeof(int) * (size_t)st.cap);
     NB_ALLOC(st.cand, sizeof(int2) * (size_t)st.cand_cap);
     if (st.ev_cap > 0) NB_ALLOC(st.ev, sizeof(EventRec) * (size_t)st.ev_cap);
@@ -649,6 +651,11 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.force_grid = force_grid;
     sp.lg_parts_override = -1;
     sp.sort_min_n = 0;
+    {
+        int variant = (params->flags >> NB_FLAG_VARIANT_SHIFT) & 0xf;
+        if (params->flags & NB_FLAG_SCALAR_FORCE) variant = 4;
+        sp.iblock = variant == 5 ? 1024 : kIBlock;
+    }
     StepDesc d;
     plan_host(&d, &sp, n);
     out->n = d.n;

@@ -22,7 +22,7 @@
 namespace nb {
 
 constexpr int kGroup = 128;                  // rows per visit-order group == reference THREADS_PER_BLOCK (src/nbody.cu:36)
-constexpr int kIBlock = 512;                 // rows per i-block == rows per force CTA (warps x 32 lanes x rows per lane)
+constexpr int kIBlock = 512;                 // default rows per i-block == rows per force CTA (warps x 32 lanes x rows per lane)
 constexpr int kTJ = 512;                     // j bodies per shared-memory tile
 constexpr int kMaxLgParts = 3;               // smallest work unit = kTJ >> 3 = 64 bodies
 constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
@@ -87,6 +87,7 @@ struct StepParams {
     int rank, world;
     int force_grid;
     int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
+    int iblock;                   // rows per i-block of the force-kernel variant in use (512 or 1024)
     int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
     int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
 };
@@ -136,9 +137,9 @@ cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStr
 cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s);
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
                           cudaStream_t s);
-int force_occupancy(int variant, int *regs, int *threads);   // resident CTAs per SM of the force kernel
-constexpr int kForceVariants = 5;
-size_t fpart_slabs(int force_grid, int shard_cap);   // slabs of 512 float2 needed
+int force_occupancy(int variant, int *regs, int *threads, int *iblock);   // resident CTAs per SM of the force kernel
+constexpr int kForceVariants = 6;
+size_t fpart_slabs(int force_grid, int shard_cap, int iblock);   // slabs of `iblock` float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
 
 }  // namespace nb

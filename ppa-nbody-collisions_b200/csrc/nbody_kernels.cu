@@ -84,9 +84,10 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.excl_len = n - d.window_len;
     const int world = p.world > 1 ? p.world : 1;
     const int rank = p.world > 1 ? p.rank : 0;
-    const int iblocks_total = (n + kIBlock - 1) / kIBlock;
+    const int IB = p.iblock > 0 ? p.iblock : kIBlock;      // rows per i-block = rows per force CTA
+    const int iblocks_total = (n + IB - 1) / IB;
     const int per_rank = (iblocks_total + world - 1) / world;
-    d.rows_per_rank = per_rank * kIBlock;
+    d.rows_per_rank = per_rank * IB;
     long long lo = (long long)rank * d.rows_per_rank;
     d.row_lo = lo < n ? (int)lo : n;
     long long hi = lo + d.rows_per_rank;
@@ -94,7 +95,7 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     if (d.row_hi < d.row_lo) d.row_hi = d.row_lo;
     d.row_act_hi = d.row_hi < d.n_active ? d.row_hi : d.n_active;
     if (d.row_act_hi < d.row_lo) d.row_act_hi = d.row_lo;
-    d.n_iblocks = (d.row_act_hi - d.row_lo + kIBlock - 1) / kIBlock;
+    d.n_iblocks = (d.row_act_hi - d.row_lo + IB - 1) / IB;
     d.n_jtiles = (n + kTJ - 1) / kTJ;
     d.force_exact = n < 2 * T ? 1 : 0;
     // Unit size.  Splitting every j-tile into 2, 4 or 8 parts keeps the static partition over the force grid
@@ -261,20 +262,15 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
 // stage refills it with the segment kStages ahead.  Inside a segment every part is a checkpoint: its sums are
 // kept only if the row's collision pre-test stayed clear over the part, otherwise the part is redone exactly.
 template <bool PACKED, int WARPS, int IPT, bool SORTED>
-__device__ __forceinline__ void force_body(const DevState &st, const StepParams &p, float *tiles_dyn)
+__device__ __forceinline__ void force_body(const DevState &st, const StepParams &p, float *tiles_dyn,
+                                           unsigned long long *full_bar, unsigned *done_cnt,
+                                           float4 (*acc_s)[WARPS * 32])
 {
-    static_assert(WARPS * 32 * IPT == kIBlock, "one CTA covers one i-block");
+    constexpr int IBLOCK = WARPS * 32 * IPT;      // rows per CTA = rows per i-block (p.iblock)
     static_assert(IPT << kMaxLgParts <= 32, "one redo bit per (part, row) of a segment");
     constexpr int THREADS = WARPS * 32;
     constexpr int WROWS = 32 * IPT;               // rows per warp (a divisor of the 128-row visit-order group)
     float(*tiles)[kSortedTileFloats] = reinterpret_cast<float(*)[kSortedTileFloats]>(tiles_dyn);   // kStages of the larger layout
-    __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ unsigned done_cnt[kStages];      // warps that finished the segment in each stage (refill trigger)
-    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per segment with a
-    // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one short
-    // float sum instead of growing with n as a single running float sum does
-    __shared__ float4 acc_s[IPT][THREADS];
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long U = st.desc->units;
     const int c = blockIdx.x;
@@ -357,7 +353,7 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
     for (int it = 0; left > 0; ++it) {
         if (it == 0 || v == 0) {
             // (re)load this warp's rows: lane l holds rows wbase + 32 q + l; gbase = their 128-row group
-            wbase = row_lo + ib * kIBlock + warp * WROWS;
+            wbase = row_lo + ib * IBLOCK + warp * WROWS;
             gbase = wbase & ~(kGroup - 1);
             warp_active = wbase < row_act_hi;
 #pragma unroll
@@ -569,7 +565,7 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
         v += parts;
         if (v == TP || left == 0) {               // leaving this i-block: flush the partial sums of this run
             if (warp_active) {
-                float2 *slab = st.fpart + (size_t)(c + ib) * kIBlock + warp * WROWS + lane;
+                float2 *slab = st.fpart + (size_t)(c + ib) * IBLOCK + warp * WROWS + lane;
 #pragma unroll
                 for (int q = 0; q < IPT; ++q) {
                     const float4 a = acc_s[q][threadIdx.x];
@@ -595,10 +591,16 @@ template <bool PACKED, int WARPS, int IPT, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState st, const StepParams p)
 {
     extern __shared__ __align__(128) float tiles_dyn[];
+    __shared__ __align__(8) unsigned long long full_bar[kStages];
+    __shared__ unsigned done_cnt[kStages];        // warps that finished the segment in each stage (refill trigger)
+    // second summation level: per row {fx_hi, fx_lo, fy_hi, fy_lo}, updated once per segment with a
+    // compensated (TwoSum) add, so the rounding error of a row's force stays at the level of one short
+    // float sum instead of growing with n as a single running float sum does
+    __shared__ float4 acc_s[IPT][WARPS * 32];
     if (st.desc->sorted)
-        force_body<PACKED, WARPS, IPT, true>(st, p, tiles_dyn);
+        force_body<PACKED, WARPS, IPT, true>(st, p, tiles_dyn, full_bar, done_cnt, acc_s);
     else
-        force_body<PACKED, WARPS, IPT, false>(st, p, tiles_dyn);
+        force_body<PACKED, WARPS, IPT, false>(st, p, tiles_dyn, full_bar, done_cnt, acc_s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -622,7 +624,8 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
         return b.z != 0.f;
     }
     // force = sum of the segment partials in CTA order
-    const int ib = local / kIBlock, within = local % kIBlock;
+    const int IB = p.iblock > 0 ? p.iblock : kIBlock;
+    const int ib = local / IB, within = local % IB;
     const long long U = d.units;
     const int TP = d.n_jtiles << d.lg_parts;
     const int G = (long long)p.force_grid < U ? p.force_grid : (int)U;
@@ -630,7 +633,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     const int c_last = unit_owner((long long)(ib + 1) * TP - 1, U, G);
     float fx = 0.f, fy = 0.f;
     for (int c = c_first; c <= c_last; ++c) {
-        const float2 part = st.fpart[(size_t)(c + ib) * kIBlock + within];
+        const float2 part = st.fpart[(size_t)(c + ib) * IB + within];
         fx += part.x;
         fy += part.y;
     }
@@ -925,6 +928,7 @@ __global__ void __launch_bounds__(128) render_kernel(const DevState st, const in
 //   2: packed,       4 warps x 4 rows/lane, <= 128 registers (4 CTAs = 16 warps per SM)
 //   3: packed,       8 warps x 2 rows/lane, <= 128 registers (2 CTAs = 16 warps per SM)
 //   4: scalar FP32,  4 warps x 4 rows/lane (A/B reference for the packed path)
+//   5: packed,       8 warps x 4 rows/lane (1024-row i-blocks), <= 128 registers (2 CTAs = 16 warps per SM)
 constexpr int kForceDynSmem = kStages * kSortedTileFloats * 4;
 
 #define NB_FORCE_VARIANTS(X)     \
@@ -932,7 +936,8 @@ constexpr int kForceDynSmem = kStages * kSortedTileFloats * 4;
     X(1, true, 8, 2, 4)          \
     X(2, true, 4, 4, 4)          \
     X(3, true, 8, 2, 2)          \
-    X(4, false, 4, 4, 4)
+    X(4, false, 4, 4, 4)         \
+    X(5, true, 8, 4, 2)
 
 }  // namespace
 
@@ -1001,15 +1006,16 @@ cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, 
     return cudaGetLastError();
 }
 
-int force_occupancy(int variant, int *regs, int *threads)
+int force_occupancy(int variant, int *regs, int *threads, int *iblock)
 {
     int occ = 0;
     cudaFuncAttributes fa = {};
-    int thr = 0;
+    int thr = 0, ibl = 0;
     switch (variant) {
 #define X(ID, PK, W, I, MB)                                                                        \
     case ID:                                                                                       \
         thr = W * 32;                                                                              \
+        ibl = W * 32 * I;                                                                          \
         cudaFuncSetAttribute(force_kernel<PK, W, I, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kForceDynSmem); \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_kernel<PK, W, I, MB>, thr, kForceDynSmem);   \
         cudaFuncGetAttributes(&fa, force_kernel<PK, W, I, MB>);                                    \
@@ -1021,12 +1027,13 @@ int force_occupancy(int variant, int *regs, int *threads)
     }
     if (regs) *regs = fa.numRegs;
     if (threads) *threads = thr;
+    if (iblock) *iblock = ibl;
     return occ;
 }
 
-size_t fpart_slabs(int force_grid, int shard_cap)
+size_t fpart_slabs(int force_grid, int shard_cap, int iblock)
 {
-    return (size_t)force_grid + (size_t)(shard_cap + kIBlock - 1) / kIBlock + 1;
+    return (size_t)force_grid + (size_t)(shard_cap + iblock - 1) / iblock + 1;
 }
 
 void plan_host(StepDesc *d, const StepParams *p, int n)

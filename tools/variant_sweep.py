@@ -16,7 +16,7 @@ from oracle import oracle as O  # noqa: E402
 
 nb = G.load_package()
 sizes = [int(a) for a in sys.argv[1:]] or [16384, 131072]
-NVAR = 5
+NVAR = 6
 
 
 def check(variant):
