@@ -76,7 +76,7 @@ typedef struct nb_params {
                                  n >= sort_min_n, every step runs on a Morton-cell-sorted copy of the bodies so that
                                  the collision pre-test is skipped for (rows, j part) pairs whose bounding boxes are
                                  apart; results keep the bodies' own order, events and survivors are unchanged     */
-#define NB_SORT_MIN_N_DEFAULT 98304
+#define NB_SORT_MIN_N_DEFAULT 65536
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
 #define NB_FLAG_VARIANT(v) ((v) << NB_FLAG_VARIANT_SHIFT)

@@ -404,7 +404,7 @@ def test_driver_checkpoint_resume(nb, tmp_path):
 @pytest.mark.parametrize("n,field,sort_min_n,steps", [(1500, 6000, 1024, 6), (3000, 12000, 2900, 6), (16384, 100000, 1024, 10),
                                                       (20000, 60000, 19000, 8)])
 def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
-    """The cell-sorted shadow order (default from 98 304 bodies on) forced on at small n: same events, survivors,
+    """The cell-sorted shadow order (default from 65 536 bodies on) forced on at small n: same events, survivors,
     masses and radii as the oracle; the second and fourth case cross the threshold while running, so steps on the
     sorted order and on the bodies' own order follow each other in both graphs."""
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
