@@ -215,8 +215,9 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.force_grid = c->sm_count * occ;
     sp.count_stats = 1;
     sp.iblock = iblock;
-    // the cell-sorted order pays for itself from about 1e5 bodies on; it needs all-pairs coverage (the reference's
-    // excluded windows are defined by body index) and is sized in only if the capacity can ever reach the threshold
+    // the cell-sorted order pays for itself from about 6e4 bodies on (profiles/r01_sort_threshold.log); it needs
+    // all-pairs coverage (the reference's excluded windows are defined by body index) and is sized in only if the
+    // capacity can ever reach the threshold
     sp.sort_min_n = 0;
     if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT)) {
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
