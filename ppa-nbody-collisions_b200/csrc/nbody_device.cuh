@@ -28,7 +28,7 @@ constexpr int kMaxLgParts = 3;               // smallest work unit = kTJ >> 3 = 
 constexpr int kTileFloats = 4 * kTJ;         // x, y, m, r planes
 constexpr int kTileBytes = kTileFloats * 4;
 constexpr int kSubPart = 64;                 // bodies per bounding box of the sorted j stream (= the smallest part)
-constexpr int kSortedTileFloats = 5 * kTJ + 4 * (kTJ / kSubPart);   // x, y, m, r, orig planes + 8 float4 boxes
+constexpr int kSortedTileFloats = 5 * kTJ + 4 * (kTJ / kSubPart + 1);   // x, y, m, r, orig planes + 8 float4 boxes + their union
 constexpr int kSC = 32;                      // j bodies per sub-chunk (granularity of the collision pre-test)
 constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;

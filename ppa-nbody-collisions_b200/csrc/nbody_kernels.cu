@@ -413,16 +413,24 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
                 // (|dx| or |dy| alone already exceeds the radius) and the loop runs without it.
                 bool may_hit = true;
                 if (sorted && !pspecial) {
-                    const float4 *boxes = reinterpret_cast<const float4 *>(tiles[stage] + 5 * kTJ) + (part0 + pp) * (jw / kSubPart);
-                    float4 bb = boxes[0];
-                    for (int k = 1; k < jw / kSubPart; ++k) {
-                        const float4 o = boxes[k];
-                        bb = make_float4(fminf(bb.x, o.x), fminf(bb.y, o.y), fmaxf(bb.z, o.z), fmaxf(bb.w, o.w));
+                    const float4 *boxes = reinterpret_cast<const float4 *>(tiles[stage] + 5 * kTJ);
+                    float4 bb;
+                    if (lgP == 0) {
+                        bb = boxes[kTJ / kSubPart];                     // the tile's own box
+                    } else {
+                        boxes += (part0 + pp) * (jw / kSubPart);
+                        bb = boxes[0];
+                        for (int k = 1; k < jw / kSubPart; ++k) {
+                            const float4 o = boxes[k];
+                            bb = make_float4(fminf(bb.x, o.x), fminf(bb.y, o.y), fmaxf(bb.z, o.z), fmaxf(bb.w, o.w));
+                        }
                     }
                     bool inside = false;
 #pragma unroll
                     for (int q = 0; q < IPT; ++q) {
-                        const float R = sqrtf(thr[q]) * 1.0002f;        // thr < 0 (inactive row): NaN, never inside
+                        // pre-test radius sqrt(thr) with a margin that covers the approximate rsqrt; thr < 0
+                        // (inactive row) gives NaN: never inside
+                        const float R = thr[q] * rsqrt_approx(thr[q]) * 1.0002f;
                         const float x = -nxi[q].x, y = -nyi[q].x;
                         inside |= (x >= bb.x - R) & (x <= bb.z + R) & (y >= bb.y - R) & (y <= bb.w + R);
                     }

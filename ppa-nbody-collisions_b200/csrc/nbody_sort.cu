@@ -150,15 +150,14 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevSt
     }
 }
 
-// sorted j-tiles + bounding boxes; slot s of the sorted order holds body sidx[0][s]
-__global__ void __launch_bounds__(256) gather_kernel(const DevState st)
+// sorted j-tiles + bounding boxes; slot s of the sorted order holds body sidx[0][s].  One block per tile.
+__global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
 {
-    __shared__ float4 s_box[8];
+    __shared__ float4 s_box[kTJ / 32];
     if (!st.desc->sorted) return;
     const int n = st.desc->n;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pad_end = (n + kTJ - 1) / kTJ * kTJ;
-    if (blockIdx.x * blockDim.x >= pad_end) return;
+    const int s = blockIdx.x * kTJ + threadIdx.x;
+    if (blockIdx.x * kTJ >= n) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 b = make_float4(kPadCoord, kPadCoord, 0.f, 0.f);
     int orig = -1;
@@ -167,13 +166,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const DevState st)
         b = st.pm[orig];
         st.sinv[orig] = s;
     }
-    float *t = st.jts + (size_t)(s / kTJ) * kSortedTileFloats + (s & (kTJ - 1));
+    float *tile = st.jts + (size_t)blockIdx.x * kSortedTileFloats;
+    float *t = tile + threadIdx.x;
     t[0] = b.x;
     t[kTJ] = b.y;
     t[2 * kTJ] = b.z;
     t[3 * kTJ] = b.w;
     t[4 * kTJ] = __int_as_float(orig);
-    // bounding box per 64 slots; pads do not count (an empty box overlaps nothing)
+    // bounding box per 64 slots and of the whole tile; pads do not count (an empty box overlaps nothing)
     const float inf = __int_as_float(0x7f800000);
     float x0 = s < n ? b.x : inf, y0 = s < n ? b.y : inf, x1 = s < n ? b.x : -inf, y1 = s < n ? b.y : -inf;
 #pragma unroll
@@ -185,12 +185,17 @@ __global__ void __launch_bounds__(256) gather_kernel(const DevState st)
     }
     if (lane == 0) s_box[warp] = make_float4(x0, y0, x1, y1);
     __syncthreads();
-    if (threadIdx.x < 4) {
+    float4 *boxes = reinterpret_cast<float4 *>(tile + 5 * kTJ);
+    if (threadIdx.x < kTJ / kSubPart) {
         const float4 a = s_box[2 * threadIdx.x], c = s_box[2 * threadIdx.x + 1];
-        const int sub = (blockIdx.x * blockDim.x) / kSubPart + threadIdx.x;      // 64-slot sub-part index
-        float4 *box = reinterpret_cast<float4 *>(st.jts + (size_t)(sub / (kTJ / kSubPart)) * kSortedTileFloats + 5 * kTJ) +
-                      (sub % (kTJ / kSubPart));
-        *box = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fmaxf(a.z, c.z), fmaxf(a.w, c.w));
+        boxes[threadIdx.x] = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fmaxf(a.z, c.z), fmaxf(a.w, c.w));
+    } else if (threadIdx.x == 32) {
+        float4 u = s_box[0];
+        for (int k = 1; k < kTJ / 32; ++k) {
+            const float4 o = s_box[k];
+            u = make_float4(fminf(u.x, o.x), fminf(u.y, o.y), fmaxf(u.z, o.z), fmaxf(u.w, o.w));
+        }
+        boxes[kTJ / kSubPart] = u;
     }
 }
 
@@ -205,7 +210,7 @@ cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s)
         radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
         radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass);
     }
-    gather_kernel<<<(st.cap + kTJ + 255) / 256, 256, 0, s>>>(st);
+    gather_kernel<<<(st.cap + kTJ - 1) / kTJ, kTJ, 0, s>>>(st);
     return cudaGetLastError();
 }
 
