@@ -196,7 +196,9 @@ def run_reference(args, out_stream) -> int:
                                        "(per-step cudaMalloc, H2D, 2 kernels, blocking D2H, host compaction); note its "
                                        "coverage drops the pairs SURVEY.md C2 lists"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0})
+            "gpu_launches": 0,
+            # for scale: the CPU restatement of the same algorithm on this box's host cores (bounded sample)
+            "cpu_port": cpu_baseline(block0, n, budget_s=6.0)})
     else:
         cb = cpu_baseline(block0, n, budget_s=20.0)
         cb["kind"] = "port"
