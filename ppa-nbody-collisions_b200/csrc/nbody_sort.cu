@@ -17,8 +17,15 @@ namespace nb {
 namespace {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortPerBlock = 2048;             // elements per radix block: 8 warps x 256 contiguous elements
-constexpr int kSortPerWarp = kSortPerBlock / (kSortThreads / 32);
+constexpr int kSortMinPerBlock = 2048;          // elements per radix block: at least 8 warps x 256 contiguous elements,
+constexpr int kSortMaxBlocks = 256;             // more when that keeps the histogram table (256 x blocks) short to scan
+
+inline int sort_per_block(int cap)
+{
+    const int per = (cap + kSortMaxBlocks - 1) / kSortMaxBlocks;
+    const int rounded = (per + 255) / 256 * 256;
+    return rounded > kSortMinPerBlock ? rounded : kSortMinPerBlock;
+}
 
 __device__ __forceinline__ unsigned spread8(unsigned v)      // abcdefgh -> 0a0b0c0d0e0f0g0h
 {
@@ -45,7 +52,8 @@ __global__ void __launch_bounds__(kSortThreads) keys_kernel(const DevState st, c
 }
 
 // histogram of one 8-bit digit per radix block: hist[bin * nblocks + block]
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const DevState st, const int src, const int shift)
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const DevState st, const int src, const int shift,
+                                                                  const int per_block)
 {
     __shared__ unsigned s_hist[256];
     if (!st.desc->sorted) return;
@@ -53,8 +61,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const DevState
     const int nblocks = gridDim.x;
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kSortPerBlock;
-    for (int k = threadIdx.x; k < kSortPerBlock; k += kSortThreads) {
+    const int base = blockIdx.x * per_block;
+    for (int k = threadIdx.x; k < per_block; k += kSortThreads) {
         const int i = base + k;
         if (i < n) atomicAdd(&s_hist[(st.skey[src][i] >> shift) & 0xffu], 1u);
     }
@@ -103,8 +111,9 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(const DevState st, con
     }
 }
 
-// stable scatter of one digit: every warp walks its 512 contiguous elements in order
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevState st, const int src, const int shift)
+// stable scatter of one digit: every warp walks its contiguous share of the block's elements in order
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevState st, const int src, const int shift,
+                                                                     const int per_block)
 {
     __shared__ unsigned s_cnt[kSortThreads / 32][256];        // per warp: digit counts, then running offsets
     if (!st.desc->sorted) return;
@@ -114,8 +123,9 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevSt
     const int dst = src ^ 1;
     for (int k = threadIdx.x; k < (kSortThreads / 32) * 256; k += kSortThreads) (&s_cnt[0][0])[k] = 0;
     __syncthreads();
-    const int wbase = blockIdx.x * kSortPerBlock + warp * kSortPerWarp;
-    for (int k = lane; k < kSortPerWarp; k += 32) {
+    const int per_warp = per_block / (kSortThreads / 32);
+    const int wbase = blockIdx.x * per_block + warp * per_warp;
+    for (int k = lane; k < per_warp; k += 32) {
         const int i = wbase + k;
         if (i < n) atomicAdd(&s_cnt[warp][(st.skey[src][i] >> shift) & 0xffu], 1u);
     }
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevSt
         }
     }
     __syncthreads();
-    for (int k = lane; k < kSortPerWarp; k += 32) {           // warp-uniform trip count
+    for (int k = lane; k < per_warp; k += 32) {               // warp-uniform trip count
         const int i = wbase + k;
         const bool valid = i < n;
         const unsigned key = valid ? st.skey[src][i] : 0u;
@@ -203,17 +213,22 @@ __global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
 
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s)
 {
-    const int nblocks = (st.cap + kSortPerBlock - 1) / kSortPerBlock;
+    const int per_block = sort_per_block(st.cap);
+    const int nblocks = (st.cap + per_block - 1) / per_block;
     keys_kernel<<<(st.cap + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s>>>(st, p);
     for (int pass = 0; pass < 2; ++pass) {
-        radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass);
+        radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
         radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass);
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
     }
     gather_kernel<<<(st.cap + kTJ - 1) / kTJ, kTJ, 0, s>>>(st);
     return cudaGetLastError();
 }
 
-size_t sort_hist_entries(int cap) { return (size_t)256 * ((cap + kSortPerBlock - 1) / kSortPerBlock); }
+size_t sort_hist_entries(int cap)
+{
+    const int per_block = sort_per_block(cap);
+    return (size_t)256 * ((cap + per_block - 1) / per_block);
+}
 
 }  // namespace nb
