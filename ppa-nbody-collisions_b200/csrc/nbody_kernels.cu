@@ -862,8 +862,10 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
         *st.desc = d;
         st.res->rmax_bits = 0u;
         st.res->ticket = 0u;
-        *st.host_n = n_new;                       // the host picks the next steps' graph by this (pinned, mapped)
-        __threadfence_system();
+        if (p.sort_min_n > 0) {                   // the host picks the next steps' graph by this (pinned, mapped);
+            *st.host_n = n_new;                   // once it has switched to the lean graph it never looks again
+            __threadfence_system();
+        }
     }
 }
 
