@@ -123,3 +123,56 @@ def test_error_codes(nb):
         nb.Simulation(0)
     with pytest.raises(nb.NbodyError):
         nb.Simulation(16, coverage=7)
+
+
+def test_every_tiling_edge_in_reference_coverage(nb, oracle):
+    """A sweep over body counts around every multiple of 128 / 129 / 512 (the reference's tile arithmetic,
+    src/nbody.cu:186-207,473, and this library's i-block, j-tile and part sizes), dense enough that collisions
+    happen at every size: 3 steps each against the oracle, one context re-used through nb_upload."""
+    sizes = sorted(set(list(range(1, 13)) + [63, 64, 65] + list(range(126, 133)) + [191, 192, 193] + list(range(254, 261)) +
+                       [383, 384, 385, 386, 387, 511, 512, 513, 514, 640, 767, 768, 769, 1023, 1024, 1025, 1151, 1152,
+                        1153, 1535, 1536, 1537, 2047, 2048, 2049]))
+    sim = nb.Simulation(max(sizes), field_w=3000, field_h=3000, coverage=nb.COVERAGE_REFERENCE, event_capacity=1 << 18)
+    par = oracle.params(field_w=3000, field_h=3000, coverage=oracle.COVERAGE_REFERENCE)
+    for n in sizes:
+        rng = np.random.default_rng(n)
+        block, _ = _random(n, 3000 * min(1.0, np.sqrt(n / 600.0)), rng)
+        sim.upload(block, n)
+        cpu, n_cpu = block.copy(), n
+        for s in range(3):
+            if n_cpu == 0:
+                break
+            sim.step(1)
+            n_cpu, _, ev_cpu = oracle.step(cpu, n_cpu, par, want_events=True)
+            got, n_gpu = sim.download()
+            ev = sim.events()
+            assert n_gpu == n_cpu, (n, s)
+            assert len(ev) == len(ev_cpu) and np.array_equal(ev["i"], ev_cpu["i"]) and np.array_equal(ev["j"], ev_cpu["j"]) \
+                and np.array_equal(ev["kind"], ev_cpu["kind"]), (n, s)
+            assert np.array_equal(got[4 * n_gpu:].view(np.uint32), cpu[4 * n_cpu:6 * n_cpu].view(np.uint32)), (n, s)
+            if n_cpu:
+                scale = max(float(np.abs(cpu[2 * n_cpu:4 * n_cpu]).max()), 1e-30)
+                assert np.abs(got[2 * n_gpu:4 * n_gpu] - cpu[2 * n_cpu:4 * n_cpu]).max() <= 1e-3 * scale, (n, s)
+    sim.close()
+
+
+def test_every_tiling_edge_in_full_coverage(nb, oracle):
+    sizes = [1, 2, 3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 1536, 2047, 2048, 2049, 3000]
+    sim = nb.Simulation(max(sizes), field_w=4000, field_h=4000, coverage=nb.COVERAGE_FULL, event_capacity=1 << 18, sort_min_n=1024)
+    par = oracle.params(field_w=4000, field_h=4000, coverage=oracle.COVERAGE_FULL)
+    for n in sizes:
+        rng = np.random.default_rng(1000 + n)
+        block, _ = _random(n, 4000 * min(1.0, np.sqrt(n / 1000.0)), rng)
+        sim.upload(block, n)
+        cpu, n_cpu = block.copy(), n
+        for s in range(3):
+            if n_cpu == 0:
+                break
+            sim.step(1)
+            n_cpu, _, ev_cpu = oracle.step(cpu, n_cpu, par, want_events=True)
+            got, n_gpu = sim.download()
+            ev = sim.events()
+            assert n_gpu == n_cpu, (n, s)
+            assert len(ev) == len(ev_cpu) and np.array_equal(ev["i"], ev_cpu["i"]) and np.array_equal(ev["j"], ev_cpu["j"]), (n, s)
+            assert np.array_equal(got[4 * n_gpu:].view(np.uint32), cpu[4 * n_cpu:6 * n_cpu].view(np.uint32)), (n, s)
+    sim.close()
