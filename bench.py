@@ -356,7 +356,8 @@ def main() -> int:
                          "peak_source": f"nameplate FP32 FMA: {sms} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz "
                                         f"(MEASURED_PEAKS.json has no FP32 entry; FFMA probe measured 73.9 TFLOP/s, "
                                         f"profiles/r01_fp32_probe.jsonl)",
-                         "share_of_step": ms_force_max / ms_total_max},
+                         "share_of_step": ms_force_max / ms_total_max,
+                         "measured_ffma_peak": 73.9, "frac_of_measured_ffma_peak": achieved_tflops / 73.9},
             "clocks": clocks,
             # force, finish, scatter (+ count when sharded or sort-capable, + 8 kernels that rebuild the cell-sorted order)
             "gpu_launches": (3 + (1 if (world > 1 or s1["culled_parts"] > s0["culled_parts"]) else 0)
