@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small driver for compute-sanitizer: a few steps at sizes that exercise every code path
+"""Small driver meant for compute-sanitizer (closed on this pool in round 1, so it was only run plain): a few steps at sizes that exercise every code path
 (tiny n / exact-only, window edges in reference coverage, part splitting, multi-segment runs, render)."""
 import sys
 from pathlib import Path
