@@ -68,6 +68,8 @@ typedef struct nb_params {
     int   world;              /* number of shards (GPUs); <= 1 means single GPU                     */
     int   flags;              /* NB_FLAG_*                                                          */
     int   sort_min_n;         /* smallest n that uses the sorted order, 0 -> NB_SORT_MIN_N_DEFAULT   */
+    float softening;          /* opt-in Plummer softening length eps: forces use |r|^2 + eps^2 (the collision
+                                 test stays unsoftened).  0 = off = the reference's arithmetic                */
 } nb_params;
 
 #define NB_FLAG_NO_GRAPH 1    /* launch kernels one by one instead of replaying a CUDA graph        */

@@ -43,6 +43,7 @@ typedef struct {
     int field_h;     /* ConfigData::fieldHeight     include/nbodyConfig.h:17 */
     int coverage;    /* ORC_COVERAGE_*                                       */
     int threads;     /* OpenMP threads, <=0 -> all                           */
+    float softening; /* opt-in Plummer softening length (NOT reference behaviour; 0 = off, the parity mode) */
 } orc_params;
 
 typedef struct {
@@ -232,6 +233,17 @@ static void eval_row(const float *pos, const float *vel, const float *mass, cons
                 if (evb) ev_push(evb, i, j, ORC_EV_KILLED);
                 continue;
             }
+            if (par->softening > 0.f) {
+                /* opt-in softened force (no reference counterpart): |r|^2 + eps^2 with the roundings of the
+                 * CUDA fast path, then the reference's formula; the collision predicate above is unsoftened */
+                const float e2 = par->softening * par->softening;
+                const float d2s = fmaf(dx, dx, fmaf(dy, dy, e2));
+                const float ds = sqrtf(d2s);
+                const float invs = 1.0f / (ds * (ds * ds));
+                fx = fmaf(invs, dx * mj, fx);
+                fy = fmaf(invs, dy * mj, fy);
+                continue;
+            }
             const float d = sqrtf(d2);                 /* :232 */
             if (!(d != 0)) ++asserts;                  /* :235 */
             const float tx = dx * mj, ty = dy * mj;    /* :239 */
@@ -344,7 +356,7 @@ void orc_rows_dv_f64(const float *block, int n, const orc_params *par, const int
                     const float rs = ri + rad[j];
                     if (d2f <= rs * rs) continue;                       /* hit: no force from j */
                     const double dx = (double)pos[2 * j] - (double)xi, dy = (double)pos[2 * j + 1] - (double)yi;
-                    const double d2 = dx * dx + dy * dy;
+                    const double d2 = dx * dx + dy * dy + (double)par->softening * (double)par->softening;
                     const double inv = 1.0 / (d2 * sqrt(d2));
                     fx += dx * (double)mass[j] * inv;
                     fy += dy * (double)mass[j] * inv;

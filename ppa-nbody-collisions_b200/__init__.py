@@ -47,7 +47,7 @@ class Params(C.Structure):
     _fields_ = [("n_max", C.c_int), ("dt", C.c_float), ("growth", C.c_float), ("field_w", C.c_int),
                 ("field_h", C.c_int), ("grav", C.c_float), ("coverage", C.c_int), ("device", C.c_int),
                 ("candidate_capacity", C.c_int), ("event_capacity", C.c_int), ("rank", C.c_int),
-                ("world", C.c_int), ("flags", C.c_int), ("sort_min_n", C.c_int)]
+                ("world", C.c_int), ("flags", C.c_int), ("sort_min_n", C.c_int), ("softening", C.c_float)]
 
 
 class Stats(C.Structure):
@@ -190,10 +190,10 @@ class Simulation:
     def __init__(self, n_max: int, dt: float = 0.2, growth: float = 0.1, field_w: int = 100000, field_h: int = 100000,
                  coverage: int = COVERAGE_REFERENCE, device: int = 0, event_capacity: int = 0,
                  candidate_capacity: int = 0, rank: int = 0, world: int = 1, flags: int = 0, grav: float = 0.0,
-                 sort_min_n: int = 0):
+                 sort_min_n: int = 0, softening: float = 0.0):
         self._h = C.c_void_p()
         self.params = Params(n_max, np.float32(dt), np.float32(growth), field_w, field_h, np.float32(grav), coverage,
-                             device, candidate_capacity, event_capacity, rank, world, flags, sort_min_n)
+                             device, candidate_capacity, event_capacity, rank, world, flags, sort_min_n, np.float32(softening))
         rc = lib().nb_create(C.byref(self._h), C.byref(self.params))
         if rc != OK:
             self._h = C.c_void_p()

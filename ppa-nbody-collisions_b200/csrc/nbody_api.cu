@@ -207,6 +207,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.dt = params->dt;
     sp.growth = params->growth;
     sp.grav = params->grav != 0.f ? params->grav : NB_GRAV_CONSTANT;
+    sp.soft2 = params->softening > 0.f ? params->softening * params->softening : 0.f;
     sp.field_w = params->field_w;
     sp.field_h = params->field_h;
     sp.coverage = params->coverage;

@@ -82,6 +82,7 @@ struct EventRec {                 // device-side event record (sorted and unpack
 
 struct StepParams {
     float dt, growth, grav;
+    float soft2;                  // squared Plummer softening length (0 = off: bit-identical to the unsoftened arithmetic)
     int field_w, field_h;
     int coverage;
     int rank, world;

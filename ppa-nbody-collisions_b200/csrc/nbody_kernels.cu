@@ -166,12 +166,12 @@ struct Window {            // the j ranges a group never visits: [a0,b0) u [a1,b
 
 template <bool PACKED, bool TEST = true>
 __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const float2 ms, const float2 nxi,
-                                      const float2 nyi, const float thr, float2 &fx, float2 &fy, bool &cand)
+                                      const float2 nyi, const float thr, const float2 soft2, float2 &fx, float2 &fy, bool &cand)
 {
     if (PACKED) {
         const float2 dx = __fadd2_rn(xs, nxi);
         const float2 dy = __fadd2_rn(ys, nyi);
-        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, soft2));     // soft2 = 0: fma(dy, dy, 0) == dy * dy
         if (TEST) {
             cand |= (d2.x <= thr);
             cand |= (d2.y <= thr);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
     } else {
         const float dx0 = xs.x + nxi.x, dy0 = ys.x + nyi.x;
         const float dx1 = xs.y + nxi.y, dy1 = ys.y + nyi.y;
-        const float d20 = fmaf(dx0, dx0, dy0 * dy0), d21 = fmaf(dx1, dx1, dy1 * dy1);
+        const float d20 = fmaf(dx0, dx0, fmaf(dy0, dy0, soft2.x)), d21 = fmaf(dx1, dx1, fmaf(dy1, dy1, soft2.y));
         if (TEST) {
             cand |= (d20 <= thr);
             cand |= (d21 <= thr);
@@ -205,7 +205,7 @@ __device__ __forceinline__ void pair2(const float2 xs, const float2 ys, const fl
 __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px, const int j0, const float xi,
                                             const float yi, const float ri, const bool active, const int row,
                                             const int excl, const Window &w, float2 &ax, float2 &ay, const int lane,
-                                            const bool sorted)
+                                            const bool sorted, const float soft2)
 {
     unsigned hits = 0;
 #pragma unroll 2
@@ -220,7 +220,7 @@ __device__ __forceinline__ void exact_chunk(const DevState &st, const float *px,
         const int j = sorted ? __float_as_int(px[4 * kTJ + jj]) : j0 + jj;
         const bool in_excl = ((j >= w.a0) & (j < w.b0)) | ((j >= w.a1) & (j < w.b1));
         const bool valid = active & (j >= 0) & (j != excl) & !in_excl;
-        const float inv = rsqrt_approx(d2);
+        const float inv = rsqrt_approx(soft2 > 0.f ? fmaf(dx, dx, fmaf(dy, dy, soft2)) : d2);   // predicate above: unsoftened
         const float s = (inv * inv) * (inv * mj);
         if (valid && !hit) {                      // even j -> .x, odd j -> .y: the fast path's lane assignment
             if (jj & 1) {
@@ -286,6 +286,7 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
     const int excl_len = st.desc->excl_len, limit_first = st.desc->limit_first;
     const bool fexact = st.desc->force_exact != 0;
     const float rmax = st.desc->rmax;
+    const float2 s2 = make_float2(p.soft2, p.soft2);
     const int jw = kTJ >> lgP;                    // bodies per part
     constexpr bool sorted = SORTED;               // cell-sorted order: 5 planes + bounding boxes per tile, rows are slots
     const float *jsrc = sorted ? st.jts : st.jt;
@@ -372,7 +373,9 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
                 nxi[q] = make_float2(-b.x, -b.x);
                 nyi[q] = make_float2(-b.y, -b.y);
                 const float rs = b.w + rmax;
-                thr[q] = act ? rs * rs : -1.0f;
+                // softened distances are larger by eps^2: so is the pre-test bound (with a margin for its rounding)
+                const float bound = p.soft2 > 0.f ? (rs * rs + p.soft2) * 1.000001f : rs * rs;
+                thr[q] = act ? bound : -1.0f;
                 fx[q] = make_float2(0.f, 0.f);
                 fy[q] = make_float2(0.f, 0.f);
                 acc_s[q][threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,9 +448,9 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
 #pragma unroll
                         for (int q = 0; q < IPT; ++q) {
                             pair2<PACKED, true>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
-                                                nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                                                nyi[q], thr[q], s2, tfx[q], tfy[q], cand[q]);
                             pair2<PACKED, true>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
-                                                nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                                                nyi[q], thr[q], s2, tfx[q], tfy[q], cand[q]);
                         }
                     }
                 } else {
@@ -459,9 +462,9 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
 #pragma unroll
                         for (int q = 0; q < IPT; ++q) {
                             pair2<PACKED, false>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nxi[q],
-                                                 nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                                                 nyi[q], thr[q], s2, tfx[q], tfy[q], cand[q]);
                             pair2<PACKED, false>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nxi[q],
-                                                 nyi[q], thr[q], tfx[q], tfy[q], cand[q]);
+                                                 nyi[q], thr[q], s2, tfx[q], tfy[q], cand[q]);
                         }
                     }
                     ++n_culled;
@@ -521,14 +524,14 @@ __device__ __forceinline__ void force_body(const DevState &st, const StepParams 
                             const float4 X = *reinterpret_cast<const float4 *>(px + 4 * k4);
                             const float4 Y = *reinterpret_cast<const float4 *>(px + kTJ + 4 * k4);
                             const float4 M = *reinterpret_cast<const float4 *>(px + 2 * kTJ + 4 * k4);
-                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nx, ny, th, tx, ty, cc);
-                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nx, ny, th, tx, ty, cc);
+                            pair2<PACKED>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(M.x, M.y), nx, ny, th, s2, tx, ty, cc);
+                            pair2<PACKED>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(M.z, M.w), nx, ny, th, s2, tx, ty, cc);
                         }
                     }
                     const bool need = mine && cc;
                     if (__any_sync(0xffffffffu, need)) {
                         ++n_exact;
-                        exact_chunk(st, px, j0, xi, yi, ri, act && need, row, excl, w, ax, ay, lane, sorted);
+                        exact_chunk(st, px, j0, xi, yi, ri, act && need, row, excl, w, ax, ay, lane, sorted, p.soft2);
                     }
                     if (mine && !cc) {
                         ax = __fadd2_rn(ax, tx);

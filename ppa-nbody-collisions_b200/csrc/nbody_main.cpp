@@ -11,6 +11,7 @@
 //   --seed S             override the seed (default 1024, :403)
 //   --scenario KIND      square (default, :401-416) | disc | two-galaxy
 //   --extent R           disc radius for disc / two-galaxy (default: fieldWidth)
+//   --softening EPS      opt-in Plummer softening length for the forces (not reference behaviour)
 //   --no-images          skip rendering and image files
 //   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
 //   --resume PATH        start from a --dump-state file instead of generating initial conditions
@@ -46,7 +47,7 @@ int main(int argc, char **argv)
     std::string config_path = "nbodyConfig.txt", dump_state, dump_events, resume, scenario = "square";
     int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
     unsigned long long seed = 1024;
-    double extent = 0;
+    double extent = 0, softening = 0;
     bool images = true;
     for (int a = 1; a < argc; ++a) {
         const std::string opt = argv[a];
@@ -68,6 +69,7 @@ int main(int argc, char **argv)
         else if (opt == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
         else if (opt == "--scenario") scenario = need("--scenario");
         else if (opt == "--extent") extent = atof(need("--extent"));
+        else if (opt == "--softening") softening = atof(need("--softening"));
         else if (opt == "--no-images") images = false;
         else if (opt == "--dump-state") dump_state = need("--dump-state");
         else if (opt == "--dump-events") dump_events = need("--dump-events");
@@ -131,6 +133,7 @@ int main(int argc, char **argv)
     par.field_h = cfg.fieldHeight;
     par.coverage = coverage;
     par.device = device;
+    par.softening = (float)softening;
     par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
     nb_ctx *ctx = nullptr;
     int rc = nb_create(&ctx, &par);

@@ -54,14 +54,14 @@ def _compare_events(ev, ev_cpu, tag):
 
 
 def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=0.1, trace=None, flags=0, resync=False,
-                      sort_min_n=0):
+                      sort_min_n=0, softening=0.0):
     sim = nb.Simulation(n0, dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage,
-                        event_capacity=max(64 * n0, 4096), flags=flags, sort_min_n=sort_min_n)
+                        event_capacity=max(64 * n0, 4096), flags=flags, sort_min_n=sort_min_n, softening=softening)
     try:
         sim.upload(block0, n0)
         cpu = block0.copy()
         n_cpu = n0
-        par = O.params(dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage)
+        par = O.params(dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage, softening=softening)
         pairs = 0
         for s in range(steps):
             if n_cpu == 0:
@@ -414,3 +414,13 @@ def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
     assert st["culled_parts"] > 0
     st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n, flags=nb.FLAG_NO_SORT)
     assert st["culled_parts"] == 0
+
+
+@pytest.mark.parametrize("n,field,coverage,sort_min_n", [(3000, 12000, 0, 0), (3000, 12000, 1, 0), (16384, 100000, 1, 1024)])
+def test_opt_in_plummer_softening(nb, oracle, n, field, coverage, sort_min_n):
+    """Opt-in physics beyond parity: forces with |r|^2 + eps^2, collision test unsoftened.  The
+    events, survivors, masses and radii are still those of the oracle run with the same softening."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    soft = _run_side_by_side(nb, oracle, block0, n, 5, coverage, field, sort_min_n=sort_min_n, softening=150.0)
+    hard = _run_side_by_side(nb, oracle, block0, n, 5, coverage, field, sort_min_n=sort_min_n)
+    assert soft["steps"] == hard["steps"] == 5
