@@ -44,6 +44,7 @@ typedef struct {
     int coverage;    /* ORC_COVERAGE_*                                       */
     int threads;     /* OpenMP threads, <=0 -> all                           */
     float softening; /* opt-in Plummer softening length (NOT reference behaviour; 0 = off, the parity mode) */
+    int merge;       /* 0: the reference's rule (src/nbody.cu:215-226).  1: opt-in conserving lowest-index merge */
 } orc_params;
 
 typedef struct {
@@ -156,6 +157,7 @@ typedef struct {
     float px, py;    /* positions[i] after MoveBodies        src/nbody.cu:288   */
     float m, r;      /* updatedMasses/Radii[i]               src/nbody.cu:245-246 */
     int hits;        /* collision pair-events seen by thread i                  */
+    int absorber;    /* merge mode 1: min(i, lowest index among i's hit partners)  */
     int asserts;     /* device asserts that would have fired src/nbody.cu:235, vec2f.h:51 */
     long long visited; /* pairs evaluated by this thread                        */
 } orc_row;
@@ -199,6 +201,7 @@ static void eval_row(const float *pos, const float *vel, const float *mass, cons
     float fx = 0.f, fy = 0.f;                          /* :153     */
     int skip = 1, deleted = 0, hits = 0, asserts = 0;  /* :178,180 */
     long long visited = 0;
+    int amin = i;
 
     for (int k = 0; k < B; ++k) {                      /* :182 */
         const int g = (int)(((long long)i + (long long)T * k) % n);   /* :186 */
@@ -221,6 +224,13 @@ static void eval_row(const float *pos, const float *vel, const float *mass, cons
             const float rs = ri + rj;
             const float rs2 = rs * rs;
             const int intersect = d2 <= rs2;
+            if (intersect && par->merge) {
+                /* conserving lowest-index merge (NOT reference behaviour): only remember the lowest partner */
+                if (j < amin) amin = j;
+                ++hits;
+                if (evb) ev_push(evb, i, j, i < j ? ORC_EV_ABSORB : ORC_EV_KILLED);
+                continue;
+            }
             if (intersect && (mi >= mj)) {             /* :215-221 */
                 umass += mj;
                 uradius = fmaf(par->growth, rj, uradius);
@@ -270,6 +280,7 @@ static void eval_row(const float *pos, const float *vel, const float *mass, cons
     out->px = fmaf(par->dt, out->vx, xi);              /* :288 */
     out->py = fmaf(par->dt, out->vy, yi);
     out->hits = hits;
+    out->absorber = amin;
     out->asserts = asserts;
     out->visited = visited;
 }
@@ -452,6 +463,46 @@ int orc_step(float *block, int n, const orc_params *par,
         vel[2 * i] = rows[i].vx; vel[2 * i + 1] = rows[i].vy;
         pos[2 * i] = rows[i].px; pos[2 * i + 1] = rows[i].py;
         mass[i] = rows[i].m; rad[i] = rows[i].r;
+    }
+    if (par->merge) {
+        /*
+         * Conserving lowest-index merge, opt-in (the north star's wording; the reference neither conserves mass
+         * nor transfers momentum).  Every body points at the lowest index among itself and its hit
+         * partners; following the pointers ends at a root; a root takes mass, momentum (at the post-force
+         * velocities) and growth * radius of everything that ends at it, in ascending index order, keeps its own
+         * position and moves on with P / M; everything else is removed.  float32, one rounding per step as written.
+         */
+        int *root = (int *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+        float *M = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+        float *Px = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+        float *Py = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+        int *members = (int *)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+        for (int i = 0; i < n; ++i) {
+            int r = i < cov.n_active ? rows[i].absorber : i;
+            while (r != (r < cov.n_active ? rows[r].absorber : r)) r = rows[r].absorber;
+            root[i] = r;
+            M[i] = mass[i];
+            Px[i] = mass[i] * vel[2 * i];
+            Py[i] = mass[i] * vel[2 * i + 1];
+        }
+        for (int k = 0; k < n; ++k) {
+            const int r = root[k];
+            if (r == k) continue;
+            ++members[r];
+            M[r] += mass[k];
+            Px[r] = fmaf(mass[k], vel[2 * k], Px[r]);
+            Py[r] = fmaf(mass[k], vel[2 * k + 1], Py[r]);
+            rad[r] = fmaf(par->growth, rad[k], rad[r]);
+        }
+        for (int k = 0; k < n; ++k) {
+            if (root[k] != k) { mass[k] = 0.f; continue; }
+            if (members[k] > 0) {                      /* a root that absorbed something */
+                vel[2 * k] = Px[k] / M[k];
+                vel[2 * k + 1] = Py[k] / M[k];
+                mass[k] = M[k];
+            }
+        }
+        free(root); free(M); free(Px); free(Py); free(members);
     }
     free(rows);
 

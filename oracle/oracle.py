@@ -26,7 +26,7 @@ EV_KILLED = 1
 
 class OrcParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("growth", C.c_float), ("field_w", C.c_int),
-                ("field_h", C.c_int), ("coverage", C.c_int), ("threads", C.c_int), ("softening", C.c_float)]
+                ("field_h", C.c_int), ("coverage", C.c_int), ("threads", C.c_int), ("softening", C.c_float), ("merge", C.c_int)]
 
 
 class OrcCov(C.Structure):
@@ -91,9 +91,9 @@ def _fptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def params(dt=0.2, growth=0.1, field_w=100000, field_h=100000, coverage=COVERAGE_REFERENCE, threads=0, softening=0.0):
+def params(dt=0.2, growth=0.1, field_w=100000, field_h=100000, coverage=COVERAGE_REFERENCE, threads=0, softening=0.0, merge=0):
     return OrcParams(np.float32(dt), np.float32(growth), int(field_w), int(field_h), int(coverage), int(threads),
-                     np.float32(softening))
+                     np.float32(softening), int(merge))
 
 
 def coverage(n: int, mode: int) -> dict:

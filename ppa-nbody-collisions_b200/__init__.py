@@ -25,7 +25,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_CANDIDATE_OVERFLOW, ERR_COMM, ERR_IO, ERR_EVENT_OVERFLOW = -1, -2, -3, -4, -5, -6, -7
 COVERAGE_REFERENCE, COVERAGE_FULL = 0, 1
 EV_ABSORB, EV_KILLED = 0, 1
-FLAG_NO_GRAPH, FLAG_SCALAR_FORCE, FLAG_NO_SORT = 1, 2, 4
+FLAG_NO_GRAPH, FLAG_SCALAR_FORCE, FLAG_NO_SORT, FLAG_MERGE_CONSERVING = 1, 2, 4, 16
 SCENARIO_SQUARE, SCENARIO_DISC, SCENARIO_TWO_GALAXY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 

@@ -127,7 +127,7 @@ static void free_all(nb_ctx *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
-    void *ptrs[] = {c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
+    void *ptrs[] = {c->st.absorber, c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
                     c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
@@ -142,6 +142,10 @@ int nb_create(nb_ctx **out, const nb_params *params)
         return NB_ERR_INVALID;
     }
     *out = nullptr;
+    if ((params->flags & NB_FLAG_MERGE_CONSERVING) && params->world > 1) {
+        set_err(nullptr, "nb_create: NB_FLAG_MERGE_CONSERVING is single-GPU only");
+        return NB_ERR_INVALID;
+    }
     if (params->n_max <= 0 || params->n_max > (1 << 26) || params->field_w <= 0 || params->field_h <= 0 ||
         (params->coverage != NB_COVERAGE_REFERENCE && params->coverage != NB_COVERAGE_FULL) ||
         (params->world > 1 && (params->rank < 0 || params->rank >= params->world))) {
@@ -216,11 +220,12 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.force_grid = c->sm_count * occ;
     sp.count_stats = 1;
     sp.iblock = iblock;
+    sp.merge = (params->flags & NB_FLAG_MERGE_CONSERVING) ? 1 : 0;
     // the cell-sorted order pays for itself from about 6e4 bodies on (profiles/r01_sort_threshold.log); it needs
     // all-pairs coverage (the reference's excluded windows are defined by body index) and is sized in only if the
     // capacity can ever reach the threshold
     sp.sort_min_n = 0;
-    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT)) {
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT) && !sp.merge) {
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (st.cap >= min_n) sp.sort_min_n = min_n;
     }
@@ -256,6 +261,11 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.cand, sizeof(int2) * (size_t)st.cand_cap);
     if (st.ev_cap > 0) NB_ALLOC(st.ev, sizeof(EventRec) * (size_t)st.ev_cap);
     NB_ALLOC(st.tile_count, sizeof(int) * ctiles);
+    if (sp.merge) {
+        NB_ALLOC(st.absorber, sizeof(int) * (size_t)st.cap);
+        NB_ALLOC(st.mhead, sizeof(int) * (size_t)st.cap);
+        NB_ALLOC(st.mnext, sizeof(int) * (size_t)st.cap);
+    }
     NB_ALLOC(st.desc, sizeof(StepDesc));
     NB_ALLOC(st.res, sizeof(StepResult));
     NB_ALLOC(st.ctr, sizeof(Counters));
@@ -275,6 +285,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     if (e == cudaSuccess) e = cudaMemsetAsync(st.res, 0, sizeof(StepResult), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.head, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.tile_count, 0, sizeof(int) * ctiles, c->stream);
+    if (e == cudaSuccess && sp.merge) e = cudaMemsetAsync(st.mhead, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
     if (e == cudaSuccess) e = launch_plan(st, sp, 0, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
@@ -382,10 +393,11 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
         const size_t chunk = (size_t)c->st.shard_cap * 24;
         NB_NCCL(c, nccl_api()->AllGather(c->st.post + (size_t)c->sp.rank * chunk, c->st.post, chunk, ncclChar, c->comm, c->stream));
     }
+    if (sp.merge) NB_CUDA(c, launch_merge(c->st, sp, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[3], c->stream));
     // a sort-capable context always runs the count kernel (it exits at once when finish already counted): the
     // step may have run on the sorted order even if THIS graph will not rebuild it
-    NB_CUDA(c, launch_compact(c->st, sp, c->sp.sort_min_n > 0, c->stream));
+    NB_CUDA(c, launch_compact(c->st, sp, c->sp.sort_min_n > 0 || sp.merge, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[4], c->stream));
     if (sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, sp, c->stream));   // shadow order of the next step
     if (marks) NB_CUDA(c, cudaEventRecord(marks[5], c->stream));

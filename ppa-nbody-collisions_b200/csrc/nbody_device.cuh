@@ -89,6 +89,7 @@ struct StepParams {
     int force_grid;
     int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
     int iblock;                   // rows per i-block of the force-kernel variant in use (512 or 1024)
+    int merge;                    // 0: the reference's absorb rule; 1: conserving lowest-index merge (opt-in)
     int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
     int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
 };
@@ -109,6 +110,8 @@ struct DevState {
     int2 *cand;
     EventRec *ev;
     int *tile_count;
+    int *absorber;                // conserving merge: lowest index among a body and its hit partners
+    int *mhead, *mnext;           //                   per-root chains of absorbed bodies
     StepDesc *desc;
     StepResult *res;
     Counters *ctr;
@@ -132,6 +135,7 @@ cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStre
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_count, cudaStream_t s);
+cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
 size_t sort_hist_entries(int cap);
 cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s);

@@ -630,6 +630,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     const float4 b = st.pm[row];
     float2 v = st.vel[row];
     if (slot >= d.row_act_hi) {                   // frozen tail: no thread in either reference kernel
+        if (p.merge) st.absorber[row] = row;
         out_pm[local] = b;
         out_vel[local] = v;
         return b.z != 0.f;
@@ -651,6 +652,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     // collision bookkeeping in the reference's visit order (src/nbody.cu:215-226)
     float umass = b.z, uradius = b.w;
     bool deleted = false;
+    int lowest = row;                             // conserving merge: lowest index among the row and its partners
     const int h = st.head[row];
     if (h >= 0) {
         st.head[row] = -1;
@@ -669,7 +671,10 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
             if (best_j < 0) break;
             const float4 o = st.pm[best_j];
             int kind;
-            if (b.z >= o.z) {                     // :215-221
+            if (p.merge) {                        // opt-in: only the pointer and the event, merge_*_kernel does the rest
+                lowest = best_j < lowest ? best_j : lowest;
+                kind = row < best_j ? NB_EV_ABSORB : NB_EV_KILLED;
+            } else if (b.z >= o.z) {              // :215-221
                 umass += o.z;
                 uradius = fmaf(p.growth, o.w, uradius);
                 kind = NB_EV_ABSORB;
@@ -688,6 +693,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
             last_key = best_key;
         }
     }
+    if (p.merge) st.absorber[row] = lowest;
     // velocity + walls (:250-264), position (:288)
     const float ax = fx * p.grav, ay = fy * p.grav;
     const float dvx = p.dt * ax, dvy = p.dt * ay;
@@ -713,12 +719,59 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     const StepDesc &d = *st.desc;
     const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     const bool survives = finish_row(st, p, d, row);
-    if (p.world <= 1 && !d.sorted) {
+    if (p.world <= 1 && !d.sorted && !p.merge) {
         // single GPU: the survivor count of the compaction tiles is taken here (saves the count kernel);
         // tile_count is zero on entry (upload / the previous scatter clear it)
         const unsigned m = __ballot_sync(0xffffffffu, survives);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st.tile_count[row / kCompactTile], __popc(m));
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// opt-in conserving lowest-index merge (NB_FLAG_MERGE_CONSERVING; not reference behaviour), single GPU,
+// bodies' own order.  finish_kernel left absorber[i]; post rows hold the post-force state of every body.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_link_kernel(const DevState st)
+{
+    const int n = st.desc->n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = i;
+    for (int a = st.absorber[r]; a != r; a = st.absorber[r]) r = a;     // pointers only ever go down: terminates
+    if (r != i) st.mnext[i] = atomicExch(&st.mhead[r], i);             // thread i onto its root's chain
+}
+
+__global__ void __launch_bounds__(256) merge_apply_kernel(const DevState st, const StepParams p)
+{
+    const int n = st.desc->n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int h = st.mhead[i];
+    if (h < 0) return;                             // not a root with members (members are zeroed by their root)
+    st.mhead[i] = -1;
+    float4 *pm = post_pm(st, 0);
+    float2 *vel = post_vel(st, 0);
+    float4 me = pm[i];
+    const float2 v = vel[i];
+    float M = me.z, Px = me.z * v.x, Py = me.z * v.y;
+    int last = -1;
+    while (true) {                                 // members in ascending index order (the chain is unordered)
+        int k = 0x7fffffff;
+        for (int e = h; e >= 0; e = st.mnext[e])
+            if (e > last && e < k) k = e;
+        if (k == 0x7fffffff) break;
+        const float4 o = pm[k];
+        const float2 ov = vel[k];
+        M += o.z;
+        Px = fmaf(o.z, ov.x, Px);
+        Py = fmaf(o.z, ov.y, Py);
+        me.w = fmaf(p.growth, o.w, me.w);
+        pm[k].z = 0.f;                             // removed by the compaction
+        last = k;
+    }
+    me.z = M;
+    pm[i] = me;
+    vel[i] = make_float2(__fdiv_rn(Px, M), __fdiv_rn(Py, M));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,7 +793,7 @@ __device__ __forceinline__ float2 load_post_vel(const DevState &st, int rpr, int
 __global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st, const StepParams p)
 {
     __shared__ int s_cnt[kCompactThreads / 32];
-    if (p.world <= 1 && !st.desc->sorted) return;      // finish_kernel already counted
+    if (p.world <= 1 && !st.desc->sorted && !p.merge) return;      // finish_kernel already counted
     const int n = st.desc->n, rpr = st.desc->rows_per_rank;
     const int base = blockIdx.x * kCompactTile;
     if (base >= n) return;
@@ -994,6 +1047,14 @@ cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_
         if (e != cudaSuccess) return e;
     }
     scatter_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s)
+{
+    const int grid = (st.cap + 255) / 256;
+    merge_link_kernel<<<grid, 256, 0, s>>>(st);
+    merge_apply_kernel<<<grid, 256, 0, s>>>(st, p);
     return cudaGetLastError();
 }
 

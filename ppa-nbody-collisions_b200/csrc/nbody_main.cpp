@@ -12,6 +12,8 @@
 //   --scenario KIND      square (default, :401-416) | disc | two-galaxy
 //   --extent R           disc radius for disc / two-galaxy (default: fieldWidth)
 //   --softening EPS      opt-in Plummer softening length for the forces (not reference behaviour)
+//   --merge MODE         reference (default, src/nbody.cu:215-226) | conserving (opt-in lowest-index merge that
+//                        conserves mass and momentum; not reference behaviour)
 //   --no-images          skip rendering and image files
 //   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
 //   --resume PATH        start from a --dump-state file instead of generating initial conditions
@@ -48,7 +50,7 @@ int main(int argc, char **argv)
     int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
     unsigned long long seed = 1024;
     double extent = 0, softening = 0;
-    bool images = true;
+    bool images = true, conserving = false;
     for (int a = 1; a < argc; ++a) {
         const std::string opt = argv[a];
         auto need = [&](const char *name) -> const char * {
@@ -70,6 +72,7 @@ int main(int argc, char **argv)
         else if (opt == "--scenario") scenario = need("--scenario");
         else if (opt == "--extent") extent = atof(need("--extent"));
         else if (opt == "--softening") softening = atof(need("--softening"));
+        else if (opt == "--merge") conserving = std::string(need("--merge")) == "conserving";
         else if (opt == "--no-images") images = false;
         else if (opt == "--dump-state") dump_state = need("--dump-state");
         else if (opt == "--dump-events") dump_events = need("--dump-events");
@@ -134,6 +137,7 @@ int main(int argc, char **argv)
     par.coverage = coverage;
     par.device = device;
     par.softening = (float)softening;
+    if (conserving) par.flags |= NB_FLAG_MERGE_CONSERVING;
     par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
     nb_ctx *ctx = nullptr;
     int rc = nb_create(&ctx, &par);

@@ -424,3 +424,37 @@ def test_opt_in_plummer_softening(nb, oracle, n, field, coverage, sort_min_n):
     soft = _run_side_by_side(nb, oracle, block0, n, 5, coverage, field, sort_min_n=sort_min_n, softening=150.0)
     hard = _run_side_by_side(nb, oracle, block0, n, 5, coverage, field, sort_min_n=sort_min_n)
     assert soft["steps"] == hard["steps"] == 5
+
+
+@pytest.mark.parametrize("n,field,coverage,steps", [(300, 1500, 1, 4), (3000, 12000, 1, 6), (3000, 12000, 0, 6), (16384, 100000, 1, 8),
+                                                    (16384, 35000, 1, 3)])
+def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps):
+    """Opt-in physics beyond parity (the north star's wording): lowest-index merge that conserves
+    mass and momentum.  Against the oracle's restatement of the same rule: events, survivors, masses and radii
+    bit-exact; and the conservation laws themselves on the CUDA result."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=coverage, event_capacity=64 * n, flags=nb.FLAG_MERGE_CONSERVING)
+    sim.upload(block0, n)
+    cpu, n_cpu = block0.copy(), n
+    par = oracle.params(field_w=field, field_h=field, coverage=coverage, merge=1)
+    plain = oracle.params(field_w=field, field_h=field, coverage=coverage)
+    merged_any = False
+    for s in range(steps):
+        # momentum right before the merge: pre-step masses times post-force velocities of every body
+        rows, _, _ = oracle.rows(cpu, n_cpu, plain, np.arange(n_cpu))
+        m_pre = cpu[4 * n_cpu:5 * n_cpu].astype(np.float64)
+        mv = m_pre[:, None] * rows[:, 0:2].astype(np.float64)
+        sim.step(1)
+        n_cpu, _, ev_cpu = oracle.step(cpu, n_cpu, par, want_events=True)
+        got, n_gpu = sim.download()
+        _compare_state(nb, oracle, got, n_gpu, cpu, n_cpu, field, f"step {s}", single_step=(s == 0))
+        _compare_events(sim.events(), ev_cpu, f"step {s}")
+        merged_any |= len(ev_cpu) > 0
+        _, vg, mg, _ = nb.split(got, n_gpu)
+        assert abs(mg.astype(np.float64).sum() - m_pre.sum()) <= 1e-6 * m_pre.sum(), f"step {s}: mass not conserved"
+        p_after = (mg.astype(np.float64)[:, None] * vg.astype(np.float64)).sum(axis=0)
+        assert (np.abs(p_after - mv.sum(axis=0)) <= 1e-5 * np.abs(mv).sum(axis=0) + 1e-30).all(), f"step {s}: momentum not conserved"
+    assert merged_any
+    sim.close()
+    with pytest.raises(nb.NbodyError):
+        nb.Simulation(n, field_w=field, field_h=field, flags=nb.FLAG_MERGE_CONSERVING, world=2, rank=0)
