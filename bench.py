@@ -359,8 +359,8 @@ def main() -> int:
                          "share_of_step": ms_force_max / ms_total_max,
                          "measured_ffma_peak": 73.9, "frac_of_measured_ffma_peak": achieved_tflops / 73.9},
             "clocks": clocks,
-            # force, finish, scatter (+ count when sharded or sort-capable, + 8 kernels that rebuild the cell-sorted order)
-            "gpu_launches": (3 + (1 if (world > 1 or s1["culled_parts"] > s0["culled_parts"]) else 0)
+            # force, finish, scatter (+ count when sharded, + 8 kernels that rebuild the cell-sorted order)
+            "gpu_launches": (3 + (1 if world > 1 else 0)
                              + (8 if s1["culled_parts"] > s0["culled_parts"] else 0)) * args.steps,
             "wall_s_timed_region": wall,
             "force": {"grid": s1["force_grid"], "regs": s1["force_regs"],

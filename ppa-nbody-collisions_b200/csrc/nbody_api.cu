@@ -395,9 +395,7 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     }
     if (sp.merge) NB_CUDA(c, launch_merge(c->st, sp, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[3], c->stream));
-    // a sort-capable context always runs the count kernel (it exits at once when finish already counted): the
-    // step may have run on the sorted order even if THIS graph will not rebuild it
-    NB_CUDA(c, launch_compact(c->st, sp, c->sp.sort_min_n > 0 || sp.merge, c->stream));
+    NB_CUDA(c, launch_compact(c->st, sp, sp.merge != 0, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[4], c->stream));
     if (sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, sp, c->stream));   // shadow order of the next step
     if (marks) NB_CUDA(c, cudaEventRecord(marks[5], c->stream));

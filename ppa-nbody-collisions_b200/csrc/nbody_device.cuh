@@ -12,7 +12,7 @@
 //                                              summed in CTA order by the finish kernel (deterministic)
 //   head [cap] int, cand[cand_cap] int2{j,next} collision candidates: one global list filled through
 //                                              warp-aggregated atomics, threaded into per-row chains
-//   tile_count[cap/1024] int                   survivors per compaction tile
+//   tile_count[cap/1024] int                   removed bodies per compaction tile of 1024 bodies
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -134,7 +134,7 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
-cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_count, cudaStream_t s);
+cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s);
 cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
 size_t sort_hist_entries(int cap);

@@ -633,6 +633,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
         if (p.merge) st.absorber[row] = row;
         out_pm[local] = b;
         out_vel[local] = v;
+        if (b.z == 0.f && p.world <= 1 && !p.merge) atomicAdd(&st.tile_count[row / kCompactTile], 1);
         return b.z != 0.f;
     }
     // force = sum of the segment partials in CTA order
@@ -711,6 +712,10 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     o.w = uradius;                                // :246
     out_pm[local] = o;
     out_vel[local] = v;
+    // single GPU: the compaction needs the number of removed bodies per tile of 1024 bodies (by body index).  They
+    // are few, so one atomic each is cheaper than a counting pass (tile_count is zero on entry: upload and the
+    // previous scatter clear it).  Sharded runs and the opt-in merge count afterwards instead (count_kernel).
+    if (!(o.z != 0.f) && p.world <= 1 && !p.merge) atomicAdd(&st.tile_count[row / kCompactTile], 1);
     return o.z != 0.f;
 }
 
@@ -718,13 +723,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
 {
     const StepDesc &d = *st.desc;
     const int row = d.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool survives = finish_row(st, p, d, row);
-    if (p.world <= 1 && !d.sorted && !p.merge) {
-        // single GPU: the survivor count of the compaction tiles is taken here (saves the count kernel);
-        // tile_count is zero on entry (upload / the previous scatter clear it)
-        const unsigned m = __ballot_sync(0xffffffffu, survives);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st.tile_count[row / kCompactTile], __popc(m));
-    }
+    finish_row(st, p, d, row);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -793,7 +792,7 @@ __device__ __forceinline__ float2 load_post_vel(const DevState &st, int rpr, int
 __global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st, const StepParams p)
 {
     __shared__ int s_cnt[kCompactThreads / 32];
-    if (p.world <= 1 && !st.desc->sorted && !p.merge) return;      // finish_kernel already counted
+    if (p.world <= 1 && !p.merge) return;          // finish_kernel already counted the removed bodies
     const int n = st.desc->n, rpr = st.desc->rows_per_rank;
     const int base = blockIdx.x * kCompactTile;
     if (base >= n) return;
@@ -801,7 +800,7 @@ __global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState s
 #pragma unroll
     for (int r = 0; r < kCompactTile / kCompactThreads; ++r) {
         const int i = base + r * kCompactThreads + threadIdx.x;
-        if (i < n) cnt += load_post_pm(st, rpr, i).z != 0.f ? 1 : 0;
+        if (i < n) cnt += load_post_pm(st, rpr, i).z != 0.f ? 0 : 1;       // removed bodies
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -857,7 +856,7 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
     const int ct = blockIdx.x, base = ct * kCompactTile;
     if (base < n) {
         int part = 0;
-        for (int t = threadIdx.x; t < ct; t += kCompactThreads) part += st.tile_count[t];
+        for (int t = threadIdx.x; t < ct; t += kCompactThreads) part += kCompactTile - st.tile_count[t];   // tiles < ct are full
         int run = block_sum(part, s_buf);
         float rmx = 0.f;
 #pragma unroll 1
@@ -901,7 +900,7 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
     const int tiles = (n + kCompactTile - 1) / kCompactTile;
     int part = 0;
     for (int t = threadIdx.x; t < tiles; t += kCompactThreads) part += __ldcg(&st.tile_count[t]);
-    const int n_new = block_sum(part, s_buf);
+    const int n_new = n - block_sum(part, s_buf);                      // tile_count holds the removed bodies
     for (int t = threadIdx.x; t < tiles; t += kCompactThreads) st.tile_count[t] = 0;   // finish_kernel adds into them
     const int pad_end = (n_new + kTJ - 1) / kTJ * kTJ;
     for (int o = n_new + threadIdx.x; o < pad_end; o += kCompactThreads) store_pad(st, o);
@@ -1038,10 +1037,10 @@ cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_compact(const DevState &st, const StepParams &p, bool always_count, cudaStream_t s)
+cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s)
 {
     const int grid = (st.cap + kCompactTile - 1) / kCompactTile;
-    if (p.world > 1 || always_count) {       // rows counted on other GPUs, or by slot instead of by index: recount
+    if (p.world > 1 || recount) {            // rows finished on other GPUs, or removed after finish (merge): count now
         count_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
