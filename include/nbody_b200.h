@@ -84,6 +84,13 @@ typedef struct nb_params {
                                  which takes mass, momentum (at the post-force velocities) and growth * radius of
                                  everything that ends at it, in ascending index order, keeps its position and moves on
                                  with P / M; the others are removed.  Events: kind = ABSORB when i < j, else KILLED   */
+#define NB_FLAG_ONE_SIDED 32   /* never use the two-sided force kernel (below)                                      */
+#define NB_FLAG_PAIR_HALVING 64 /* steps that run on the cell-sorted order (single GPU) evaluate every unordered pair
+                                 once and apply the force to both bodies (Newton's third law): 12 instead of 2 x 9
+                                 packed operations per pair of interactions.  The collision predicate is symmetric bit
+                                 for bit (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged;
+                                 force sums differ from the one-sided kernel only in rounding and summation order, and
+                                 are deterministic (every partial sum has one writer and a fixed order)            */
 #define NB_SORT_MIN_N_DEFAULT 65536
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
@@ -112,6 +119,8 @@ typedef struct nb_stats {
     int32_t force_threads;    /* threads per CTA of the force kernel                                */
     int32_t force_variant;    /* force-kernel variant in use                                        */
     int64_t culled_parts;     /* j parts that ran without the collision pre-test (sorted stream)    */
+    int32_t pair_halving;     /* 1: the next step will run the two-sided force kernel               */
+    int32_t sym_regs;         /* registers per thread of the two-sided force kernel (0: not in use) */
 } nb_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

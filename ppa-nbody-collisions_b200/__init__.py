@@ -26,6 +26,7 @@ ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_CANDIDATE_OVERFLOW, ERR_COMM, ERR_IO, E
 COVERAGE_REFERENCE, COVERAGE_FULL = 0, 1
 EV_ABSORB, EV_KILLED = 0, 1
 FLAG_NO_GRAPH, FLAG_SCALAR_FORCE, FLAG_NO_SORT, FLAG_MERGE_CONSERVING = 1, 2, 4, 16
+FLAG_ONE_SIDED, FLAG_PAIR_HALVING = 32, 64
 SCENARIO_SQUARE, SCENARIO_DISC, SCENARIO_TWO_GALAXY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 
@@ -55,7 +56,8 @@ class Stats(C.Structure):
                 ("fast_chunks", C.c_int64), ("n", C.c_int32), ("overflow", C.c_int32), ("events_dropped", C.c_int32),
                 ("sm_count", C.c_int32), ("force_grid", C.c_int32), ("force_regs", C.c_int32),
                 ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("force_threads", C.c_int32),
-                ("force_variant", C.c_int32), ("culled_parts", C.c_int64)]
+                ("force_variant", C.c_int32), ("culled_parts", C.c_int64),
+                ("pair_halving", C.c_int32), ("sym_regs", C.c_int32)]
 
 
 class Plan(C.Structure):

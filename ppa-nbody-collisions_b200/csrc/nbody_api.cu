@@ -20,6 +20,9 @@
 
 using namespace nb;
 
+// the two-sided (pair-halving) force kernel is used wherever it applies unless NB_FLAG_ONE_SIDED is given
+static constexpr bool kPairHalvingDefault = true;
+
 struct nb_ctx {
     nb_params par;
     DevState st;
@@ -27,6 +30,7 @@ struct nb_ctx {
     int device;
     int sm_count;
     int force_regs;
+    int sym_regs;
     int variant;
     int force_threads;
     cudaStream_t stream;
@@ -128,7 +132,7 @@ static void free_all(nb_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
     void *ptrs[] = {c->st.absorber, c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
-                    c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.head, c->st.cand,
+                    c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.part, c->st.xbuf, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -229,6 +233,18 @@ int nb_create(nb_ctx **out, const nb_params *params)
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (st.cap >= min_n) sp.sort_min_n = min_n;
     }
+    // two-sided force kernel on the sorted order
+    sp.sym = 0;
+    sp.sym_grid = 0;
+    sp.sym_qmax = world >= 4 ? kSymQMaxSharded : kSymQMax;
+    if (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
+        ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) {
+        const int socc = force_sym_occupancy(&c->sym_regs);
+        if (socc > 0) {
+            sp.sym = 1;
+            sp.sym_grid = c->sm_count * socc;
+        }
+    }
     sp.lg_parts_override = -1;
     if (const char *e = getenv("NBODY_B200_LG_PARTS")) sp.lg_parts_override = atoi(e) < 0 ? -1 : (atoi(e) > kMaxLgParts ? kMaxLgParts : atoi(e));   // tuning only
 
@@ -256,6 +272,17 @@ int nb_create(nb_ctx **out, const nb_params *params)
         NB_ALLOC(st.shist, sizeof(unsigned) * sort_hist_entries(st.cap));
         NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
     }
+    if (sp.sym) {
+        st.part_stride = tiles * kTJ;
+        NB_ALLOC(st.part, sizeof(float2) * st.part_stride * (size_t)std::min<size_t>(sp.sym_qmax, tiles));
+        if (world > 1) {
+            // candidate pairs one rank may contribute per step: its share of the pairs, with room for crowded starts
+            st.x_cap = params->candidate_capacity > 0 ? params->candidate_capacity : std::max(131072, st.cap / 4);
+            st.x_stride = (st.part_stride * sizeof(float2) + sizeof(XHeader) + (size_t)st.x_cap * sizeof(int2) + 255) / 256 * 256;
+            NB_ALLOC(st.xbuf, st.x_stride * (size_t)world);
+            st.cand_cap = (int)std::min<long long>(std::max<long long>(st.cand_cap, (long long)world * st.x_cap), 1LL << 30);
+        }
+    }
     NB_ALLOC(st.fpart, sizeof(float2) * iblock * fpart_slabs(sp.force_grid, st.shard_cap, iblock));
     NB_ALLOC(st.head, sizeof(int) * (size_t)st.cap);
     NB_ALLOC(st.cand, sizeof(int2) * (size_t)st.cand_cap);
@@ -273,6 +300,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
 #undef NB_ALLOC
     c->sp_plain = sp;
     c->sp_plain.sort_min_n = 0;
+    c->sp_plain.sym = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->host_n, sizeof(int), cudaHostAllocMapped);
     if (e == cudaSuccess) {
@@ -387,6 +415,12 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     NB_CUDA(c, launch_force(c->st, sp, c->variant, c->stream));
     if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[1], c->stream));
+    if (sp.sym && sp.sort_min_n > 0 && c->sp.world > 1) {
+        // two-sided kernel on several GPUs: every rank holds a part of every body's force and candidates
+        NB_CUDA(c, launch_sym_reduce(c->st, sp, c->stream));
+        NB_NCCL(c, nccl_api()->AllGather(c->st.xbuf + (size_t)c->sp.rank * c->st.x_stride, c->st.xbuf, c->st.x_stride, ncclChar, c->comm, c->stream));
+        NB_CUDA(c, launch_sym_chain(c->st, sp, c->stream));
+    }
     NB_CUDA(c, launch_finish(c->st, sp, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[2], c->stream));
     if (c->sp.world > 1) {
@@ -552,6 +586,8 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->force_regs = c->force_regs;
     out->force_threads = c->force_threads;
     out->force_variant = c->variant;
+    out->pair_halving = d.sym;
+    out->sym_regs = c->sp.sym ? c->sym_regs : 0;
     out->row_lo = d.row_lo;
     out->row_hi = d.row_hi;
     return NB_OK;

@@ -12,6 +12,9 @@
 //                                              summed in CTA order by the finish kernel (deterministic)
 //   head [cap] int, cand[cand_cap] int2{j,next} collision candidates: one global list filled through
 //                                              warp-aggregated atomics, threaded into per-row chains
+//   part [<=256][tiles*512] float2            two-sided force kernel: part[Y][slot] = force on the body in `slot` of the
+//                                              cell-sorted order from the bodies of super-tile Y (each written by
+//                                              exactly one block of the pair triangle; summed over Y by finish)
 //   tile_count[cap/1024] int                   removed bodies per compaction tile of 1024 bodies
 #pragma once
 #include <cuda_runtime.h>
@@ -33,6 +36,8 @@ constexpr int kSC = 32;                      // j bodies per sub-chunk (granular
 constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
 constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
+constexpr int kSymQMax = 256;                // two-sided force kernel: super-tiles per side of the pair triangle (at most);
+constexpr int kSymQMaxSharded = 512;         //   finer blocks when the triangle is dealt out to 4 or more GPUs
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
 constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
 
@@ -52,6 +57,9 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
     int lg_parts;                 // a work unit is kTJ >> lg_parts bodies of one j-tile (0 .. kMaxLgParts)
     int sorted;                   // 1: the force kernel streams the cell-sorted j-tiles (jts) this step
+    int sym;                      // 1: this step runs the two-sided (pair-halving) force kernel on the sorted order
+    int sym_S, sym_Q;             //    tiles per super-tile, super-tiles (Q = ceil(T / S) <= kSymQMax)
+    int sym_blocks;               //    Q (Q + 1) / 2 blocks of the pair triangle
     long long units;              // U = n_iblocks * T << lg_parts  (work units of this rank)
     float rmax;                   // max radius over live bodies
     unsigned step;                // steps since upload
@@ -60,6 +68,7 @@ struct StepDesc {                 // rewritten on the device at the end of every
 struct StepResult {               // accumulated by the scatter kernel, consumed by plan
     unsigned rmax_bits;
     unsigned ticket;
+    unsigned sym_next;            // work queue of the two-sided force kernel: next block of the pair triangle
 };
 
 struct Counters {
@@ -92,6 +101,9 @@ struct StepParams {
     int merge;                    // 0: the reference's absorb rule; 1: conserving lowest-index merge (opt-in)
     int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
     int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
+    int sym;                      // 1: steps on the cell-sorted order evaluate each unordered pair once (two-sided kernel)
+    int sym_grid;                 //    its grid (resident CTAs x SMs)
+    int sym_qmax;                 //    upper bound of sym_Q (sizes `part`)
 };
 
 struct DevState {
@@ -106,6 +118,14 @@ struct DevState {
     unsigned *shist;              // 256 x radix blocks
     unsigned char *post;          // world chunks of shard_cap * 24 B
     float2 *fpart;
+    float2 *part;                 // two-sided kernel: [sym_Q][part_stride]
+    size_t part_stride;           //                   slots per super-tile row (tiles * 512)
+    // two-sided kernel on several GPUs: every rank evaluates its share of the triangle's blocks, so forces and
+    // collision candidates of a body are spread over the ranks.  One allgather of `xbuf` per step brings them
+    // together: per rank {float2 F[part_stride]; XHeader; int2 {row, partner}[x_cap]}
+    unsigned char *xbuf;
+    size_t x_stride;              // bytes per rank region
+    int x_cap;                    // candidate pairs a rank can contribute per step
     int *head;
     int2 *cand;
     EventRec *ev;
@@ -121,6 +141,23 @@ struct DevState {
     int ev_cap;
 };
 
+struct XHeader {
+    unsigned count;               // candidate pairs this rank found this step
+    unsigned pad[3];
+};
+__host__ __device__ inline float2 *x_force(const DevState &st, int rank)
+{
+    return reinterpret_cast<float2 *>(st.xbuf + (size_t)rank * st.x_stride);
+}
+__host__ __device__ inline XHeader *x_header(const DevState &st, int rank)
+{
+    return reinterpret_cast<XHeader *>(st.xbuf + (size_t)rank * st.x_stride + st.part_stride * sizeof(float2));
+}
+__host__ __device__ inline int2 *x_pairs(const DevState &st, int rank)
+{
+    return reinterpret_cast<int2 *>(st.xbuf + (size_t)rank * st.x_stride + st.part_stride * sizeof(float2) + sizeof(XHeader));
+}
+
 __host__ __device__ inline float4 *post_pm(const DevState &st, int rank)
 {
     return reinterpret_cast<float4 *>(st.post + (size_t)rank * st.shard_cap * 24);
@@ -134,6 +171,8 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
+cudaError_t launch_sym_reduce(const DevState &st, const StepParams &p, cudaStream_t s);   // sharded two-sided kernel: before ...
+cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s);    // ... and after the allgather of xbuf
 cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s);
 cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
@@ -143,6 +182,7 @@ cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t 
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
                           cudaStream_t s);
 int force_occupancy(int variant, int *regs, int *threads, int *iblock);   // resident CTAs per SM of the force kernel
+int force_sym_occupancy(int *regs);                                       // same for the two-sided kernel
 constexpr int kForceVariants = 6;
 size_t fpart_slabs(int force_grid, int shard_cap, int iblock);   // slabs of `iblock` float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
