@@ -337,35 +337,56 @@ def main() -> int:
         sm_max = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_FALLBACK))
         sms = s1["sm_count"]
         peak_tflops = sms * 128 * 2 * sm_max * 1e6 / 1e12
+        # issue-slot bound of the two-sided kernel: 12 packed ops (2 dispatch cycles each) + 2 MUFU + 2.5 SHFL per lane
+        # give 4 ordered interactions; one dispatch per cycle and SM sub-partition, 32 lanes
+        sym_bound = 32 * 4 / 28.5 * 4 * sms * sm_max * 1e6
+        two_sided = bool(s1["pair_halving"])
+        sorted_order = s1["culled_parts"] > s0["culled_parts"]
         achieved_tflops = FLOP_PER_INTERACTION * (pairs_local / args.steps) / (ms_force_max / args.steps * 1e-3) / 1e12
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total_max / args.steps, "steps_per_sec": args.steps / (ms_total_max * 1e-3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n), "bodies": n, "coverage": "full",
-                       "parallelism": f"i-block row shards x{world} + NCCL allgather of post-step rows" if world > 1 else "1 GPU",
+                       "parallelism": (f"pair-triangle blocks dealt round-robin to {world} GPUs + NCCL allgather of partial forces, "
+                                       f"candidate pairs and post-step rows") if world > 1 else "1 GPU",
                        "l2": "flushed between timed iterations (256 MiB memset); each step timed by its own CUDA-event pair",
                        "bodies_after": s1["n"]},
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak_tflops, "traffic": ncu_traffic_bytes(n),
                          "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_force_1m_ncu.json); algorithmic HBM bytes of "
-                                         "the launch are 32 n (one pass over the 16 B/body i rows and j tiles): the kernel is "
-                                         "FP32-issue bound, not HBM bound",
-                         "kernel": "force_kernel<packed f32x2, 8 warps x 2 rows/lane>", "ms_per_launch": ms_force_max / args.steps,
+                                         "the launch are 32 n (one pass over the 16 B/body rows and sorted tiles) plus, for the "
+                                         "two-sided kernel, one write of the per-super-tile partial sums (8 B x 256 per body): "
+                                         "the kernel is FP32-issue bound, not HBM bound",
+                         "kernel": ("force_sym_kernel<packed f32x2, 8 warps x 4 rows/lane, two-sided>" if two_sided
+                                    else "force_kernel<packed f32x2, 8 warps x 2 rows/lane>"),
+                         "ms_per_launch": ms_force_max / args.steps,
                          "flop_per_interaction": FLOP_PER_INTERACTION,
                          "peak_source": f"nameplate FP32 FMA: {sms} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz "
                                         f"(MEASURED_PEAKS.json has no FP32 entry; FFMA probe measured 73.9 TFLOP/s, "
                                         f"profiles/r01_fp32_probe.jsonl)",
                          "share_of_step": ms_force_max / ms_total_max,
-                         "measured_ffma_peak": 73.9, "frac_of_measured_ffma_peak": achieved_tflops / 73.9},
+                         "measured_ffma_peak": 73.9, "frac_of_measured_ffma_peak": achieved_tflops / 73.9,
+                         "pair_halving": two_sided,
+                         "note": ("achieved = 20 flop x ORDERED interactions / time, the reference's accounting (SURVEY 8d). The "
+                                  "two-sided kernel evaluates each unordered pair once (12 packed f32x2 operations + 2 MUFU + 2.5 "
+                                  "SHFL per lane for 4 ordered interactions, against 2 x 9 + 2 x 2 one-sided), so frac can pass 1; "
+                                  "against its own issue-slot bound (28.5 dispatch cycles per 128 ordered interactions and SM "
+                                  f"sub-partition = {sym_bound / 1e12:.2f}e12 interactions/s) it reaches frac_of_issue_bound")
+                                 if two_sided else "achieved = 20 flop x ordered interactions / time (SURVEY 8d)",
+                         "frac_of_issue_bound": ((pairs_local / args.steps) / (ms_force_max / args.steps * 1e-3) / sym_bound
+                                                 if two_sided else None)},
             "clocks": clocks,
-            # force, finish, scatter (+ count when sharded, + 8 kernels that rebuild the cell-sorted order)
-            "gpu_launches": (3 + (1 if world > 1 else 0)
-                             + (8 if s1["culled_parts"] > s0["culled_parts"] else 0)) * args.steps,
+            # force, finish, scatter; + count when sharded; + 8 kernels that rebuild the cell-sorted order and the second
+            # force kernel of a sort-capable step (the one the step does not use returns at once); + partial-force
+            # reduction and candidate threading around the exchange of the sharded two-sided kernel
+            "gpu_launches": (3 + (1 if world > 1 else 0) + (8 if sorted_order else 0) + (1 if two_sided else 0)
+                             + (2 if two_sided and world > 1 else 0)) * args.steps,
             "wall_s_timed_region": wall,
             "force": {"grid": s1["force_grid"], "regs": s1["force_regs"],
                       "fast_chunks": s1["fast_chunks"] - s0["fast_chunks"], "exact_chunks": s1["exact_chunks"] - s0["exact_chunks"],
-                      "parts_without_pretest": s1["culled_parts"] - s0["culled_parts"], "cell_sorted_order": s1["culled_parts"] > s0["culled_parts"]},
+                      "parts_without_pretest": s1["culled_parts"] - s0["culled_parts"], "cell_sorted_order": sorted_order,
+                      "two_sided": two_sided, "two_sided_regs": s1["sym_regs"]},
             "collision_events": s1["candidates"] - s0["candidates"],
         }
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))

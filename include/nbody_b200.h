@@ -91,7 +91,7 @@ typedef struct nb_params {
                                  for bit (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged;
                                  force sums differ from the one-sided kernel only in rounding and summation order, and
                                  are deterministic (every partial sum has one writer and a fixed order)            */
-#define NB_SORT_MIN_N_DEFAULT 65536
+#define NB_SORT_MIN_N_DEFAULT 40960
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
 #define NB_FLAG_VARIANT(v) ((v) << NB_FLAG_VARIANT_SHIFT)

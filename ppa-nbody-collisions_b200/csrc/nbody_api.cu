@@ -236,7 +236,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     // two-sided force kernel on the sorted order
     sp.sym = 0;
     sp.sym_grid = 0;
-    sp.sym_qmax = world >= 4 ? kSymQMaxSharded : kSymQMax;
+    sp.sym_qmax = world >= 2 ? kSymQMaxSharded : kSymQMax;
     if (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
         ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) {
         const int socc = force_sym_occupancy(&c->sym_regs);

@@ -37,7 +37,7 @@ constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
 constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
 constexpr int kSymQMax = 256;                // two-sided force kernel: super-tiles per side of the pair triangle (at most);
-constexpr int kSymQMaxSharded = 512;         //   finer blocks when the triangle is dealt out to 4 or more GPUs
+constexpr int kSymQMaxSharded = 512;         //   finer blocks when the triangle is dealt out to several GPUs
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
 constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
 

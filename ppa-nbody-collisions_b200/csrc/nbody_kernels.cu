@@ -644,6 +644,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
 // Results go to part[Y][slot] (Y = super-tile of the other side); each entry has exactly one writer block and
 // a fixed summation order, so the forces do not depend on which CTA took which block.
 // ------------------------------------------------------------------------------------------------
+#ifndef NB_SYM_UNROLL
+#define NB_SYM_UNROLL 32
+#endif
+constexpr int kSymUnroll = NB_SYM_UNROLL;   // sub-steps per iteration of the ring loop
 constexpr int kSymIPT = 4;
 constexpr int kSymThreads = 256;
 constexpr int kSymDynSmem = kStages * kSortedTileFloats * 4;
@@ -655,7 +659,7 @@ __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms,
                                              float2 (&tfx)[kSymIPT], float2 (&tfy)[kSymIPT], bool &cand, const int lane)
 {
     const int src = (lane + 1) & 31;
-#pragma unroll 4
+#pragma unroll kSymUnroll
     for (int s = 0; s < 32; ++s) {
 #pragma unroll
         for (int q = 0; q < kSymIPT; ++q) {
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
     };
 
     unsigned it = 0;                              // tile pairs this CTA has consumed: ring position and parity
-    unsigned n_fast = 0, n_exact = 0, n_culled = 0;
+    unsigned n_exact = 0, n_culled = 0;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -902,6 +906,25 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
                 thr[q] = __float_as_int(rows[4 * kTJ + rs]) >= 0 ? bound : -1.0f;      // pads never flag
                 acc_s[q][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            // row-side sums of the rounds since the last fold (registers); banked in the compensated shared
+            // accumulators before every pre-tested round and at the end of every tile pair
+            float2 tfx[kSymIPT], tfy[kSymIPT];
+#pragma unroll
+            for (int q = 0; q < kSymIPT; ++q) {
+                tfx[q] = make_float2(0.f, 0.f);
+                tfy[q] = make_float2(0.f, 0.f);
+            }
+            auto fold_rows = [&]() {
+#pragma unroll
+                for (int q = 0; q < kSymIPT; ++q) {
+                    float4 a = acc_s[q][tid];
+                    two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
+                    two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
+                    acc_s[q][tid] = a;
+                    tfx[q] = make_float2(0.f, 0.f);
+                    tfy[q] = make_float2(0.f, 0.f);
+                }
+            };
             float4 rb;                            // bounding box of this warp's 128 rows
             {
                 const float4 *bx = reinterpret_cast<const float4 *>(rows + 5 * kTJ);
@@ -924,43 +947,36 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
                     float2 ys = *reinterpret_cast<const float2 *>(tl + kTJ + 64 * c + 2 * lane);
                     float2 ms = *reinterpret_cast<const float2 *>(tl + 2 * kTJ + 64 * c + 2 * lane);
                     float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
-                    float2 tfx[kSymIPT], tfy[kSymIPT];
-#pragma unroll
-                    for (int q = 0; q < kSymIPT; ++q) {
-                        tfx[q] = make_float2(0.f, 0.f);
-                        tfy[q] = make_float2(0.f, 0.f);
-                    }
                     bool cand = false;
                     if (may_hit) {
+                        // the round's row sums must be separable (they are dropped if the pre-test fires):
+                        // bank what earlier rounds left in the registers first
+                        fold_rows();
                         sym_substeps<true>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
                     } else {
                         sym_substeps<false>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
                         ++n_culled;
                     }
-                    n_fast += 2;
                     if (may_hit && __any_sync(0xffffffffu, cand)) {
                         // rare: a possible hit somewhere in the round; its sums are dropped and the round redone
                         sym_exact_round(st, tl, rows, c, k, own, p.soft2, p.rank, acc_s, gacc[buf]);
                         n_exact += 2;
-                    } else {
 #pragma unroll
                         for (int q = 0; q < kSymIPT; ++q) {
-                            float4 a = acc_s[q][tid];
-                            two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
-                            two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
-                            acc_s[q][tid] = a;
+                            tfx[q] = make_float2(0.f, 0.f);
+                            tfy[q] = make_float2(0.f, 0.f);
                         }
-                        if (!own) {
-                            float4 ga = gacc[buf][32 * c + lane];
-                            ga.x += gx.x;
-                            ga.y += gx.y;
-                            ga.z += gy.x;
-                            ga.w += gy.y;
-                            gacc[buf][32 * c + lane] = ga;
-                        }
+                    } else if (!own) {
+                        float4 ga = gacc[buf][32 * c + lane];
+                        ga.x += gx.x;
+                        ga.y += gx.y;
+                        ga.z += gy.x;
+                        ga.w += gy.y;
+                        gacc[buf][32 * c + lane] = ga;
                     }
                     __syncthreads();
                 }
+                fold_rows();
                 // every warp is done with the stage: refill it with the tile pair kStages ahead
                 if (tid == 0 && pmore) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -982,6 +998,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
                 }
             }
             // i side of the finished row of tile pairs: the two warps that share these rows, in fixed order
+            __syncthreads();
             if (h == 0) {
                 float2 *dst = st.part + (size_t)C * stride + (size_t)I * kTJ + 128 * k + lane;
 #pragma unroll
@@ -1002,7 +1019,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         }
     }
     if (p.count_stats && lane == 0) {
-        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)n_fast);
+        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)it * 8ull);        // 4 rounds x 2 sub-chunks of 32 bodies
         atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_exact);
         atomicAdd(&st.ctr->culled_parts, (unsigned long long)n_culled);
     }

@@ -404,7 +404,7 @@ def test_driver_checkpoint_resume(nb, tmp_path):
 @pytest.mark.parametrize("n,field,sort_min_n,steps", [(1500, 6000, 1024, 6), (3000, 12000, 2900, 6), (16384, 100000, 1024, 10),
                                                       (20000, 60000, 19000, 8)])
 def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
-    """The cell-sorted shadow order (default from 65 536 bodies on) forced on at small n: same events, survivors,
+    """The cell-sorted shadow order (default from 40 960 bodies on) forced on at small n: same events, survivors,
     masses and radii as the oracle; the second and fourth case cross the threshold while running, so steps on the
     sorted order and on the bodies' own order follow each other in both graphs."""
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
@@ -414,6 +414,57 @@ def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
     assert st["culled_parts"] > 0
     st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n, flags=nb.FLAG_NO_SORT)
     assert st["culled_parts"] == 0
+    # the one-sided kernel on the sorted order (what steps on the sorted order ran before the two-sided kernel)
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field, sort_min_n=sort_min_n, flags=nb.FLAG_ONE_SIDED)
+    assert st["culled_parts"] > 0 and st["sym_regs"] == 0
+
+
+@pytest.mark.parametrize("n,field,steps,softening", [(1100, 4000, 4, 0.0), (3000, 9000, 6, 0.0), (5000, 20000, 6, 0.0),
+                                                     (20000, 30000, 4, 0.0), (20000, 60000, 6, 0.0), (5000, 20000, 5, 500.0)])
+def test_two_sided_force_kernel(nb, oracle, n, field, steps, softening):
+    """Pair halving (every unordered pair evaluated once, force applied to both bodies; default on the sorted order),
+    forced on at small n and at surface densities up to 20x the shipped one: events, survivors, masses and radii
+    bit-exact against the oracle, trajectories within the usual tolerances, with and without softening."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, sort_min_n=1024)
+    sim.upload(block0, n)
+    assert sim.stats()["pair_halving"] == 1 and sim.stats()["sym_regs"] > 0
+    sim.close()
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field, sort_min_n=1024, softening=softening)
+    assert st["exact_chunks"] > 0 and st["culled_parts"] > 0
+    st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, sort_min_n=1024, softening=softening,
+                           flags=nb.FLAG_NO_GRAPH | nb.FLAG_PAIR_HALVING)
+    assert st["exact_chunks"] > 0
+
+
+def test_two_sided_is_deterministic_and_agrees_with_one_sided(nb):
+    """N = 131 072 disc at the shipped surface density, 4 steps: two runs of the two-sided kernel are bit-identical
+    (every partial sum has one writer and a fixed order although blocks are taken from a queue), and against the
+    one-sided kernel the events, survivors, masses and radii are identical and velocities agree to 1e-4 max|v|."""
+    n = 131072
+    R = 1e5 * np.sqrt(n / 16384.0)
+    field = int(R)
+    block0 = nb.generate(nb.SCENARIO_DISC, n, extent=R, field_w=field, field_h=field)
+    out = []
+    for flags in (0, 0, nb.FLAG_ONE_SIDED):
+        sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, flags=flags, event_capacity=1 << 20)
+        sim.upload(block0, n)
+        assert sim.stats()["pair_halving"] == (0 if flags else 1)
+        sim.step(4)
+        got, n1 = sim.download()
+        out.append((got, n1, sim.events()))
+        sim.close()
+    (a, na, ea), (b, nb_, eb), (c, nc, ec) = out
+    assert na == nb_ and np.array_equal(a.view(np.uint32), b.view(np.uint32)), "two runs of the two-sided kernel differ"
+    assert np.array_equal(ea, eb)
+    assert na == nc and len(ea) == len(ec)
+    for key in ("step", "i", "j", "kind"):
+        assert np.array_equal(ea[key], ec[key]), f"events differ from the one-sided kernel in {key}"
+    pa, va, ma, ra = nb.split(a, na)
+    pc, vc, mc, rc = nb.split(c, nc)
+    assert np.array_equal(ma.view(np.uint32), mc.view(np.uint32)) and np.array_equal(ra.view(np.uint32), rc.view(np.uint32))
+    assert np.abs(va - vc).max() <= 1e-4 * np.abs(vc).max()
+    assert np.abs(pa - pc).max() <= 1e-5 * field
 
 
 @pytest.mark.parametrize("n,field,coverage,sort_min_n", [(3000, 12000, 0, 0), (3000, 12000, 1, 0), (16384, 100000, 1, 1024)])
