@@ -390,9 +390,14 @@ def main() -> int:
             "collision_events": s1["candidates"] - s0["candidates"],
         }
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic bytes per body: finish reads pm 16 + vel 8 + one partial-sum slab 8 and writes 24;
+        # algorithmic bytes per body: finish reads pm 16 + vel 8 + one partial-sum slab 8 (one-sided) and writes 24;
         # compaction reads 24 (+ 16 for the count pass when sharded) and writes pm 16 + vel 8 + j-tile 16
-        fin_b, cmp_b = 56.0, (64.0 if world == 1 else 80.0)
+        # the two-sided kernel leaves one 8-B partial per super-tile (one GPU) or per rank (after the exchange)
+        tiles = (n + 511) // 512
+        qmax = 256 if world == 1 else 512
+        sym_S = (tiles + qmax - 1) // qmax
+        sym_Q = (tiles + sym_S - 1) // sym_S
+        fin_b, cmp_b = 56.0 + (8.0 * (sym_Q if world == 1 else world) - 8.0 if two_sided else 0.0), (64.0 if world == 1 else 80.0)
         out["hbm_kernels"] = {
             "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
             "finish": {"ms_per_launch": prof["finish"] / prof_steps, "bytes_per_body": fin_b,
@@ -401,7 +406,8 @@ def main() -> int:
                         "achieved_gbs": cmp_b * n_mid / (prof["compact"] / prof_steps * 1e-3) / 1e9},
             "allgather_ms": prof["allgather"] / prof_steps,
             "sort_ms": prof["sort"] / prof_steps,
-            "note": "O(n) kernels, < 0.02 % of the step at this n: launch/latency bound rather than bandwidth bound",
+            "note": "O(n) kernels, < 0.2 % of the step at this n; on several GPUs `finish` also spans the partial-force "
+                    "reduction, the exchange (NCCL allgather) and the candidate threading of the two-sided kernel",
         }
         for k in ("finish", "compact"):
             out["hbm_kernels"][k]["frac"] = out["hbm_kernels"][k]["achieved_gbs"] / hbm_peak

@@ -1040,14 +1040,26 @@ __global__ void __launch_bounds__(256) sym_reduce_kernel(const DevState st, cons
     if (!d.sym) return;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= d.n) return;
-    const int X = slot / kTJ / d.sym_S, Q = d.sym_Q;
+    const int X = slot / kTJ / d.sym_S, Q = d.sym_Q, W = p.world, me = p.rank;
     float fx = 0.f, fy = 0.f, lx = 0.f, ly = 0.f;
     const float2 *src = st.part + slot;
-    for (int y = 0; y < Q; ++y) {
-        if (sym_block_index(X, y, Q) % p.world != p.rank) continue;
+    auto add = [&](int y) {
         const float2 v = __ldcs(src + (size_t)y * st.part_stride);
         two_sum(fx, lx, v.x);
         two_sum(fy, ly, v.y);
+    };
+    // super-tiles before X: block (y, X) has index y (Q - 1) - y (y - 1) / 2 + X - y - 1, stepping by Q - 2 - y
+    int b = X - 1;
+    for (int y = 0; y < X; ++y) {
+        if (b % W == me) add(y);
+        b += Q - 2 - y;
+    }
+    if (sym_block_index(X, X, Q) % W == me) add(X);
+    // super-tiles after X: block (X, y), consecutive indices, so every W-th one is this rank's
+    if (X + 1 < Q) {
+        const int b0 = sym_block_index(X, X + 1, Q);
+        int first = (me - b0 % W + W) % W;
+        for (int y = X + 1 + first; y < Q; y += W) add(y);
     }
     x_force(st, p.rank)[slot] = make_float2(fx + lx, fy + ly);
 }
