@@ -273,6 +273,12 @@ int nb_create(nb_ctx **out, const nb_params *params)
         NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
     }
     if (sp.sym) {
+        // the two-sided kernel keeps one partial sum per body and super-tile: a fixed budget (a rule every rank of
+        // a sharded run evaluates alike) decides whether the capacity is worth it; beyond it the one-sided kernel runs
+        const size_t part_bytes = sizeof(float2) * tiles * kTJ * std::min<size_t>(sp.sym_qmax, tiles);
+        if (part_bytes > ((size_t)48 << 30)) sp.sym = 0;
+    }
+    if (sp.sym) {
         st.part_stride = tiles * kTJ;
         NB_ALLOC(st.part, sizeof(float2) * st.part_stride * (size_t)std::min<size_t>(sp.sym_qmax, tiles));
         if (world > 1) {
