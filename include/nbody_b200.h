@@ -187,8 +187,17 @@ typedef struct nb_plan {
     int32_t n, blocks, limit_last, limit_first, n_active, window_len;
     int32_t row_lo, row_hi, row_act_hi, rows_per_rank, n_iblocks, n_jtiles;
     int64_t units;
+    int32_t sorted;           /* 1: the step runs on the cell-sorted order                                   */
+    int32_t two_sided;        /* 1: ... with the two-sided force kernel: the triangle of tile pairs in blocks */
+    int32_t sym_S, sym_Q;     /*    of sym_S x sym_S tile pairs, sym_Q super-tiles per side                   */
+    int32_t sym_blocks;       /*    sym_Q (sym_Q + 1) / 2 blocks; rank r of W takes blocks r, r + W, ...      */
+    int32_t reserved;
 } nb_plan;
 int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out);
+/* Block b (queue order) of the two-sided kernel's pair triangle with Q super-tiles per side -> (R, C), R <= C;
+   nb_plan_block_index is its inverse (any order of the two super-tiles).  Host only. */
+int nb_plan_block(int Q, int b, int *R, int *C);
+int nb_plan_block_index(int Q, int X, int Y);
 
 /* ---- render (src/nbody.cu:294-348, 350-371) ------------------------------ */
 /* Rasterise the current bodies into a w*h 8-bit image (background 254, body 0). */

@@ -34,7 +34,7 @@ UNIQUE_ID_BYTES = 128
 SYMBOLS = [
     "nb_create", "nb_destroy", "nb_last_error", "nb_version", "nb_upload", "nb_download", "nb_num_bodies",
     "nb_step", "nb_step_timed", "nb_step_profile", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
-    "nb_plan_host", "nb_render", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
+    "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_render", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
     "nb_rng_fval_range", "nb_generate",
 ]
 
@@ -63,7 +63,8 @@ class Stats(C.Structure):
 class Plan(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "blocks", "limit_last", "limit_first", "n_active", "window_len",
                                           "row_lo", "row_hi", "row_act_hi", "rows_per_rank", "n_iblocks", "n_jtiles")]
-    _fields_ = _fields_ + [("units", C.c_int64)]
+    _fields_ = _fields_ + [("units", C.c_int64)] + [(k, C.c_int32) for k in ("sorted", "two_sided", "sym_S", "sym_Q",
+                                                                              "sym_blocks", "reserved")]
 
 
 class Config(C.Structure):
@@ -131,6 +132,8 @@ def lib() -> C.CDLL:
     L.nb_comm_unique_id.argtypes = [vp]
     L.nb_comm_init.argtypes = [vp, vp]
     L.nb_plan_host.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(Plan)]
+    L.nb_plan_block.argtypes = [C.c_int, C.c_int, ip, ip]
+    L.nb_plan_block_index.argtypes = [C.c_int, C.c_int, C.c_int]
     L.nb_render.argtypes = [vp, vp, C.c_int, C.c_int]
     L.nb_write_pgm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
     L.nb_config_parse.argtypes = [C.c_char_p, C.POINTER(Config), C.c_int]
@@ -169,13 +172,28 @@ def parse_config(path: str, echo_fd: int = -1) -> tuple[int, Config]:
     return rc, cfg
 
 
-def plan(n: int, coverage: int = COVERAGE_FULL, rank: int = 0, world: int = 1, force_grid: int = 592) -> dict:
-    p = Params(n_max=max(n, 1), coverage=coverage, rank=rank, world=world, field_w=1, field_h=1)
+def plan(n: int, coverage: int = COVERAGE_FULL, rank: int = 0, world: int = 1, force_grid: int = 592, flags: int = 0,
+         sort_min_n: int = 0, n_max: int = 0) -> dict:
+    p = Params(n_max=max(n, n_max, 1), coverage=coverage, rank=rank, world=world, field_w=1, field_h=1, flags=flags,
+               sort_min_n=sort_min_n)
     out = Plan()
     rc = lib().nb_plan_host(C.byref(p), n, force_grid, C.byref(out))
     if rc != OK:
         raise NbodyError("nb_plan_host", rc, "invalid arguments")
     return {k: getattr(out, k) for k, _ in Plan._fields_}
+
+
+def plan_block(Q: int, b: int):
+    """(R, C), R <= C: super-tiles of block b in the two-sided kernel's queue order."""
+    R, Cc = C.c_int(), C.c_int()
+    rc = lib().nb_plan_block(Q, b, C.byref(R), C.byref(Cc))
+    if rc != OK:
+        raise NbodyError("nb_plan_block", rc, "invalid arguments")
+    return R.value, Cc.value
+
+
+def plan_block_index(Q: int, X: int, Y: int) -> int:
+    return lib().nb_plan_block_index(Q, X, Y)
 
 
 def split(block: np.ndarray, n: int):

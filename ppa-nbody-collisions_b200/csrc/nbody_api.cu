@@ -704,7 +704,16 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.rank = params->world > 1 ? params->rank : 0;
     sp.force_grid = force_grid;
     sp.lg_parts_override = -1;
+    // the same rules as nb_create (without the device-dependent parts: occupancy, memory budget)
+    sp.merge = (params->flags & NB_FLAG_MERGE_CONSERVING) ? 1 : 0;
     sp.sort_min_n = 0;
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT) && !sp.merge) {
+        const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
+        if (params->n_max >= min_n) sp.sort_min_n = min_n;
+    }
+    sp.sym_qmax = sp.world >= 2 ? kSymQMaxSharded : kSymQMax;
+    sp.sym = (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
+              ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) ? 1 : 0;
     {
         int variant = (params->flags >> NB_FLAG_VARIANT_SHIFT) & 0xf;
         if (params->flags & NB_FLAG_SCALAR_FORCE) variant = 4;
@@ -712,6 +721,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     }
     StepDesc d;
     plan_host(&d, &sp, n);
+    memset(out, 0, sizeof(*out));
     out->n = d.n;
     out->blocks = d.blocks;
     out->limit_last = d.limit_last;
@@ -725,7 +735,25 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     out->n_iblocks = d.n_iblocks;
     out->n_jtiles = d.n_jtiles;
     out->units = d.units;
+    out->sorted = d.sorted;
+    out->two_sided = d.sym;
+    out->sym_S = d.sym_S;
+    out->sym_Q = d.sym_Q;
+    out->sym_blocks = d.sym_blocks;
     return NB_OK;
+}
+
+int nb_plan_block(int Q, int b, int *R, int *C)
+{
+    if (!R || !C || Q <= 0 || b < 0 || b >= Q * (Q + 1) / 2) return NB_ERR_INVALID;
+    sym_block_host(b, Q, R, C);
+    return NB_OK;
+}
+
+int nb_plan_block_index(int Q, int X, int Y)
+{
+    if (Q <= 0 || X < 0 || Y < 0 || X >= Q || Y >= Q) return NB_ERR_INVALID;
+    return sym_block_index_host(X, Y, Q);
 }
 
 }  // extern "C"

@@ -186,5 +186,7 @@ int force_sym_occupancy(int *regs);                                       // sam
 constexpr int kForceVariants = 6;
 size_t fpart_slabs(int force_grid, int shard_cap, int iblock);   // slabs of `iblock` float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
+void sym_block_host(int b, int Q, int *R, int *C);         // two-sided kernel: block b of the queue order -> super-tiles (R, C)
+int sym_block_index_host(int X, int Y, int Q);             //                   and back
 
 }  // namespace nb

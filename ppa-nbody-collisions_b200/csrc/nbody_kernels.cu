@@ -644,6 +644,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) force_kernel(const DevState 
 // Results go to part[Y][slot] (Y = super-tile of the other side); each entry has exactly one writer block and
 // a fixed summation order, so the forces do not depend on which CTA took which block.
 // ------------------------------------------------------------------------------------------------
+// Blocks of the pair triangle in queue order: the Q (Q - 1) / 2 full-size blocks (R < C), row by row, then the Q
+// half-size diagonal ones (a short tail).  sym_block_index is the inverse of sym_block_decode.
+__host__ __device__ inline void sym_block_decode(int b, int Q, int &R, int &C)
+{
+    const int noff = Q * (Q - 1) / 2;
+    if (b >= noff) {
+        R = C = b - noff;
+        return;
+    }
+    int r = 0, rem = b;
+    while (rem >= Q - 1 - r) {
+        rem -= Q - 1 - r;
+        ++r;
+    }
+    R = r;
+    C = r + 1 + rem;
+}
+__host__ __device__ inline int sym_block_index(int X, int Y, int Q)
+{
+    const int R = X < Y ? X : Y, C = X < Y ? Y : X;
+    if (R == C) return Q * (Q - 1) / 2 + R;
+    return R * (Q - 1) - R * (R - 1) / 2 + (C - R - 1);
+}
+
 #ifndef NB_SYM_UNROLL
 #define NB_SYM_UNROLL 32
 #endif
@@ -849,21 +873,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             // several GPUs: rank r takes blocks r, r + world, ... of the same order
             const long long b = (long long)atomicAdd(&st.res->sym_next, 1u) * p.world + p.rank;
             int R = -1, C = -1;
-            if (b < nblk) {
-                // full-size blocks (R < C) first, the half-size diagonal ones last: a short tail
-                const int noff = Q * (Q - 1) / 2;
-                if (b >= noff) {
-                    R = C = (int)(b - noff);
-                } else {
-                    int r = 0, rem = (int)b;
-                    while (rem >= Q - 1 - r) {
-                        rem -= Q - 1 - r;
-                        ++r;
-                    }
-                    R = r;
-                    C = r + 1 + rem;
-                }
-            }
+            if (b < nblk) sym_block_decode((int)b, Q, R, C);
             s_rc[0] = R;
             s_rc[1] = C;
         }
@@ -1027,13 +1037,6 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
 
 // Sharded two-sided kernel, before the allgather: this rank's partial force on every slot = the sum, in
 // super-tile order, of the part[][] entries its own blocks wrote.
-__device__ __forceinline__ int sym_block_index(int X, int Y, int Q)
-{
-    const int R = X < Y ? X : Y, C = X < Y ? Y : X;
-    if (R == C) return Q * (Q - 1) / 2 + R;
-    return R * (Q - 1) - R * (R - 1) / 2 + (C - R - 1);
-}
-
 __global__ void __launch_bounds__(256) sym_reduce_kernel(const DevState st, const StepParams p)
 {
     const StepDesc &d = *st.desc;
@@ -1636,6 +1639,16 @@ size_t fpart_slabs(int force_grid, int shard_cap, int iblock)
 void plan_host(StepDesc *d, const StepParams *p, int n)
 {
     plan_fill(*d, *p, n, 0.f, 0u);
+}
+
+void sym_block_host(int b, int Q, int *R, int *C)
+{
+    sym_block_decode(b, Q, *R, *C);
+}
+
+int sym_block_index_host(int X, int Y, int Q)
+{
+    return sym_block_index(X, Y, Q);
 }
 
 }  // namespace nb

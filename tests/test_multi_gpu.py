@@ -29,7 +29,8 @@ def _gpu_count() -> int:
         return 0
 
 
-def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int, steps: int, out_dir: str, sort_min_n: int = 0):
+def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int, steps: int, out_dir: str, sort_min_n: int = 0,
+            flags: int = 0):
     sys.path.insert(0, str(ROOT))
     import torch
     import torch.distributed as dist
@@ -43,7 +44,7 @@ def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int
     dist.broadcast_object_list(ids, src=0)
     block0 = nb.generate(nb.SCENARIO_SQUARE, n0, field_w=field, field_h=field)
     sim = nb.Simulation(n0, field_w=field, field_h=field, coverage=coverage, device=rank, rank=rank, world=world,
-                        event_capacity=64 * n0, sort_min_n=sort_min_n)
+                        event_capacity=64 * n0, sort_min_n=sort_min_n, flags=flags)
     sim.comm_init(ids[0])
     sim.upload(block0, n0)
     states = []
@@ -60,12 +61,15 @@ def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("n0,field,coverage,sort_min_n", [(16384, 100000, 0, 0), (16384, 100000, 1, 0), (3000, 12000, 1, 0),
-                                                         (700, 3000, 0, 0), (16384, 100000, 1, 1024), (3000, 12000, 1, 2900)])
-def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage, sort_min_n):
+# flags 32 = NB_FLAG_ONE_SIDED: the sorted order with row shards; without it steps on the sorted order run the two-sided
+# kernel (blocks of the pair triangle dealt to the ranks, exchange of partial forces and candidate pairs)
+@pytest.mark.parametrize("n0,field,coverage,sort_min_n,flags", [(16384, 100000, 0, 0, 0), (16384, 100000, 1, 0, 0), (3000, 12000, 1, 0, 0),
+                                                               (700, 3000, 0, 0, 0), (16384, 100000, 1, 1024, 0), (3000, 12000, 1, 2900, 0),
+                                                               (16384, 100000, 1, 1024, 32), (20000, 30000, 1, 1024, 0)])
+def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage, sort_min_n, flags):
     import torch.multiprocessing as mp
     world, steps = 2, 4
-    mp.spawn(_worker, args=(world, _free_port(), n0, field, coverage, steps, str(tmp_path), sort_min_n), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n0, field, coverage, steps, str(tmp_path), sort_min_n, flags), nprocs=world, join=True)
     block = nb.generate(nb.SCENARIO_SQUARE, n0, field_w=field, field_h=field)
     par = oracle.params(field_w=field, field_h=field, coverage=coverage)
     n = n0

@@ -99,3 +99,51 @@ def test_plan_shards_cover_all_rows(nb):
                     active += p["row_act_hi"] - p["row_lo"]
                 assert lo_prev == n
                 assert active == nb.plan(n, coverage=cov)["n_active"]
+
+
+def test_two_sided_plan_covers_every_tile_pair_once(nb):
+    """Host logic of the two-sided force kernel: which steps use it, the cut of the pair triangle into blocks, and the
+    deal of the blocks to the ranks -- every unordered tile pair belongs to exactly one block of exactly one rank."""
+    for n, world in ((1023, 1), (40959, 1), (40960, 1), (49152, 1), (131072, 1), (1048576, 1), (4194304, 1), (1000003, 2),
+                     (1048576, 8), (4194304, 8), (70000, 3)):
+        plans = [nb.plan(n, coverage=nb.COVERAGE_FULL, rank=r, world=world) for r in range(world)]
+        p = plans[0]
+        uses = n >= 40960
+        assert p["sorted"] == int(uses) and p["two_sided"] == int(uses), (n, world, p)
+        if not uses:
+            continue
+        T, S, Q = p["n_jtiles"], p["sym_S"], p["sym_Q"]
+        assert T == (n + 511) // 512 and Q <= (256 if world == 1 else 512) and (Q - 1) * S < T <= Q * S
+        assert p["sym_blocks"] == Q * (Q + 1) // 2
+        assert all(q["sym_S"] == S and q["sym_Q"] == Q and q["sym_blocks"] == p["sym_blocks"] for q in plans)
+        if Q > 64:
+            Q_check = range(0, p["sym_blocks"], 97)          # sample: the full enumeration is done for small Q below
+        else:
+            Q_check = range(p["sym_blocks"])
+        for b in Q_check:
+            R, C = nb.plan_block(Q, b)
+            assert 0 <= R <= C < Q and nb.plan_block_index(Q, R, C) == b and nb.plan_block_index(Q, C, R) == b
+    for Q in (1, 2, 3, 7, 33):
+        seen = {}
+        for b in range(Q * (Q + 1) // 2):
+            R, C = nb.plan_block(Q, b)
+            assert (R, C) not in seen
+            seen[(R, C)] = b
+        assert len(seen) == Q * (Q + 1) // 2 and all(R <= C for R, C in seen)
+        # the half-size diagonal blocks come last (a short tail of the queue)
+        assert sorted(seen[(R, R)] for R in range(Q)) == list(range(Q * (Q - 1) // 2, Q * (Q + 1) // 2))
+        for world in (1, 2, 3, 8):
+            owner = {rc: b % world for rc, b in seen.items()}
+            load = [sum(1 for o in owner.values() if o == r) for r in range(world)]
+            assert max(load) - min(load) <= 1
+
+
+def test_two_sided_plan_flags(nb):
+    assert nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["two_sided"] == 0 and nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["sorted"] == 1
+    assert nb.plan(131072, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(131072, flags=nb.FLAG_NO_SORT)["two_sided"] == 0
+    assert nb.plan(131072, coverage=nb.COVERAGE_REFERENCE)["two_sided"] == 0
+    assert nb.plan(5000, sort_min_n=1024)["two_sided"] == 1 and nb.plan(1023, sort_min_n=1)["two_sided"] == 0
+    assert nb.plan(30000, n_max=131072)["two_sided"] == 0            # a big context whose body count has dropped
+    assert nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["sorted"] == 0
+    with pytest.raises(nb.NbodyError):
+        nb.plan_block(4, 10)
