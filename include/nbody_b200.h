@@ -62,7 +62,10 @@ typedef struct nb_params {
     int   coverage;           /* NB_COVERAGE_*                                                      */
     int   device;             /* CUDA device ordinal                                                */
     int   candidate_capacity; /* entries of the per-step collision candidate list (ordered hit
-                                 pairs), 0 -> max(4 * n_max, 64Ki)                                  */
+                                 pairs), 0 -> max(4 * n_max, 64Ki).  With the two-sided kernel on
+                                 several GPUs it is also the number of pairs ONE rank can contribute
+                                 to the per-step exchange, 0 -> max(128Ki, n_max / 4); exceeding
+                                 either is reported as NB_ERR_CANDIDATE_OVERFLOW                     */
     int   event_capacity;     /* 0 = no event log; else records kept between nb_events() calls      */
     int   rank;               /* this context's shard, 0 <= rank < world                            */
     int   world;              /* number of shards (GPUs); <= 1 means single GPU                     */

@@ -14,6 +14,7 @@
 //   --softening EPS      opt-in Plummer softening length for the forces (not reference behaviour)
 //   --merge MODE         reference (default, src/nbody.cu:215-226) | conserving (opt-in lowest-index merge that
 //                        conserves mass and momentum; not reference behaviour)
+//   --one-sided          never use the two-sided (pair-halving) force kernel (full coverage, >= 40960 bodies)
 //   --no-images          skip rendering and image files
 //   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
 //   --resume PATH        start from a --dump-state file instead of generating initial conditions
@@ -50,7 +51,7 @@ int main(int argc, char **argv)
     int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
     unsigned long long seed = 1024;
     double extent = 0, softening = 0;
-    bool images = true, conserving = false;
+    bool images = true, conserving = false, one_sided = false;
     for (int a = 1; a < argc; ++a) {
         const std::string opt = argv[a];
         auto need = [&](const char *name) -> const char * {
@@ -73,6 +74,7 @@ int main(int argc, char **argv)
         else if (opt == "--extent") extent = atof(need("--extent"));
         else if (opt == "--softening") softening = atof(need("--softening"));
         else if (opt == "--merge") conserving = std::string(need("--merge")) == "conserving";
+        else if (opt == "--one-sided") one_sided = true;
         else if (opt == "--no-images") images = false;
         else if (opt == "--dump-state") dump_state = need("--dump-state");
         else if (opt == "--dump-events") dump_events = need("--dump-events");
@@ -138,6 +140,7 @@ int main(int argc, char **argv)
     par.device = device;
     par.softening = (float)softening;
     if (conserving) par.flags |= NB_FLAG_MERGE_CONSERVING;
+    if (one_sided) par.flags |= NB_FLAG_ONE_SIDED;
     par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
     nb_ctx *ctx = nullptr;
     int rc = nb_create(&ctx, &par);
