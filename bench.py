@@ -129,6 +129,7 @@ def cpu_baseline(block0: np.ndarray, n: int, budget_s: float = 12.0) -> dict:
     same workload: every row costs n-1 pair evaluations, so rows x (n-1) / time is the port's rate."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
+    budget_s = float(os.environ.get("NBODY_BENCH_CPU_BUDGET_S", budget_s))     # tests shorten the sample
     par = O.params(field_w=FIELD, field_h=FIELD, coverage=O.COVERAGE_FULL, threads=cores)
     rng = np.random.default_rng(1)
     probe = np.sort(rng.choice(n, size=min(n, 64 * cores), replace=False)).astype(np.int32)
