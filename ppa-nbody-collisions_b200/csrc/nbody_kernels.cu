@@ -1074,7 +1074,9 @@ __global__ void __launch_bounds__(256) sym_chain_kernel(const DevState st, const
     if (!d.sym) return;
     unsigned mine = 0;
     for (int r = 0; r < p.world; ++r) {
-        const unsigned cnt = min(x_header(st, r)->count, (unsigned)st.x_cap);
+        const unsigned found = x_header(st, r)->count;
+        if (found > (unsigned)st.x_cap && blockIdx.x == 0 && threadIdx.x == 0) st.ctr->overflow_flag = 1;   // every rank reports it
+        const unsigned cnt = min(found, (unsigned)st.x_cap);
         const int2 *src = x_pairs(st, r);
         for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
             const int2 pr = src[e];
