@@ -10,6 +10,9 @@
 //     per (row, j pair), TWO ordered interactions per evaluation.
 // two-sided, shared: same, but the j pair is read from shared memory at a rotating index and its accumulators are
 //     read-modify-written in a per-warp private shared array (no SHFL).
+// two-sided, hybrid (not measured yet, prepared for the next round): positions and masses are re-read from a doubled
+//     copy of the chunk in shared memory at a rotating offset (3 LDS.64, immediate offsets once unrolled), only the
+//     four accumulator registers travel by SHFL: 7 instead of 10 issue slots per sub-step.
 // "ginter_per_s" counts ORDERED interactions in every variant.
 #include <cstdio>
 #include <cstdlib>
@@ -25,13 +28,15 @@ __device__ __forceinline__ float rsqrt_ftz(float x)
 }
 
 constexpr int TJ = 512;
-enum Mode { ONE_SIDED = 0, SYM_SHFL = 1, SYM_SHFL_NOTEST = 2, SYM_LDS = 3, ONE_SIDED_NOTEST = 4 };
+enum Mode { ONE_SIDED = 0, SYM_SHFL = 1, SYM_SHFL_NOTEST = 2, SYM_LDS = 3, ONE_SIDED_NOTEST = 4, SYM_HYB = 5 };
 
 template <int IPT, int MODE, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_sym(float *out, int reps)
 {
     __shared__ __align__(16) float sx[TJ], sy[TJ], sm[TJ];
     __shared__ __align__(16) float4 sg[MODE == SYM_LDS ? THREADS / 32 : 1][MODE == SYM_LDS ? TJ / 2 : 1];
+    // SYM_HYB: per warp, the chunk's 32 (x, y, m) pairs twice in a row, so that lane + s never wraps
+    __shared__ __align__(16) float2 dup[MODE == SYM_HYB ? THREADS / 32 : 1][3][MODE == SYM_HYB ? 64 : 1];
     for (int k = threadIdx.x; k < TJ; k += blockDim.x) {
         sx[k] = 1000.f + 37.f * k; sy[k] = -500.f + 11.f * k; sm[k] = 1e10f + k;
     }
@@ -82,9 +87,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k_sym(float *out, int reps)
                     ys = *reinterpret_cast<const float2 *>(&sy[cc * 64 + 2 * lane]);
                     ms = *reinterpret_cast<const float2 *>(&sm[cc * 64 + 2 * lane]);
                 }
-#pragma unroll 4
+                if (MODE == SYM_HYB) {
+                    __syncwarp();
+                    dup[warp][0][lane] = xs; dup[warp][0][lane + 32] = xs;
+                    dup[warp][1][lane] = ys; dup[warp][1][lane + 32] = ys;
+                    dup[warp][2][lane] = ms; dup[warp][2][lane + 32] = ms;
+                    __syncwarp();
+                }
+#pragma unroll(MODE == SYM_HYB ? 32 : 4)
                 for (int s = 0; s < 32; ++s) {
                     int slot = 0;
+                    if (MODE == SYM_HYB) {
+                        xs = dup[warp][0][lane + s];
+                        ys = dup[warp][1][lane + s];
+                        ms = dup[warp][2][lane + s];
+                    }
                     if (MODE == SYM_LDS) {
                         slot = cc * 32 + ((lane + s) & 31);
                         xs = *reinterpret_cast<const float2 *>(&sx[2 * slot]);
@@ -111,6 +128,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_sym(float *out, int reps)
                     }
                     if (MODE == SYM_LDS) {
                         sg[warp][slot] = make_float4(gx.x, gx.y, gy.x, gy.y);
+                    } else if (MODE == SYM_HYB) {
+                        const int src = (lane + 1) & 31;
+                        gx.x = __shfl_sync(0xffffffffu, gx.x, src); gx.y = __shfl_sync(0xffffffffu, gx.y, src);
+                        gy.x = __shfl_sync(0xffffffffu, gy.x, src); gy.y = __shfl_sync(0xffffffffu, gy.y, src);
                     } else {
                         const int src = (lane + 1) & 31;
                         xs.x = __shfl_sync(0xffffffffu, xs.x, src); xs.y = __shfl_sync(0xffffffffu, xs.y, src);
@@ -185,6 +206,10 @@ int main()
     SW(SYM_SHFL, "sym_shfl")
     SW(SYM_SHFL_NOTEST, "sym_shfl_notest")
     SW(SYM_LDS, "sym_lds")
+    SW(SYM_HYB, "sym_hybrid")
+    run<8, SYM_SHFL, 256, 2>("sym_shfl", out, sms);          // 8 rows per lane: 1.25 SHFL per evaluation, 16 warps per SM
+    run<8, SYM_SHFL_NOTEST, 256, 2>("sym_shfl_notest", out, sms);
+    run<8, SYM_HYB, 256, 2>("sym_hybrid", out, sms);
     CK(cudaFree(out));
     return 0;
 }
