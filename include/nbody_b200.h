@@ -94,6 +94,10 @@ typedef struct nb_params {
                                  for bit (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged;
                                  force sums differ from the one-sided kernel only in rounding and summation order, and
                                  are deterministic (every partial sum has one writer and a fixed order)            */
+#define NB_FLAG_SYM_ROWS8 128  /* tuning variant of the two-sided kernel: 8 rows per lane at 2 CTAs per SM (half the
+                                 shuffles per evaluation).  Same results as the default (4 rows, 3 CTAs); measured 3 %
+                                 slower at n = 262 144 (profiles/r01_two_sided_rows8.log) although the bare loop is 7 %
+                                 faster: kept for tuning, never selected by default                                  */
 #define NB_SORT_MIN_N_DEFAULT 40960
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */

@@ -26,7 +26,7 @@ ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_CANDIDATE_OVERFLOW, ERR_COMM, ERR_IO, E
 COVERAGE_REFERENCE, COVERAGE_FULL = 0, 1
 EV_ABSORB, EV_KILLED = 0, 1
 FLAG_NO_GRAPH, FLAG_SCALAR_FORCE, FLAG_NO_SORT, FLAG_MERGE_CONSERVING = 1, 2, 4, 16
-FLAG_ONE_SIDED, FLAG_PAIR_HALVING = 32, 64
+FLAG_ONE_SIDED, FLAG_PAIR_HALVING, FLAG_SYM_ROWS8 = 32, 64, 128
 SCENARIO_SQUARE, SCENARIO_DISC, SCENARIO_TWO_GALAXY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 

@@ -239,7 +239,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.sym_qmax = world >= 2 ? kSymQMaxSharded : kSymQMax;
     if (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
         ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) {
-        const int socc = force_sym_occupancy(&c->sym_regs);
+        sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
+        const int socc = force_sym_occupancy(sp.sym_rows, &c->sym_regs);
         if (socc > 0) {
             sp.sym = 1;
             sp.sym_grid = c->sm_count * socc;

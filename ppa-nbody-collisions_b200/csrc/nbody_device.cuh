@@ -104,6 +104,7 @@ struct StepParams {
     int sym;                      // 1: steps on the cell-sorted order evaluate each unordered pair once (two-sided kernel)
     int sym_grid;                 //    its grid (resident CTAs x SMs)
     int sym_qmax;                 //    upper bound of sym_Q (sizes `part`)
+    int sym_rows;                 //    rows per lane: 4 (default), 8 (NB_FLAG_SYM_ROWS8)
 };
 
 struct DevState {
@@ -182,7 +183,7 @@ cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t 
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
                           cudaStream_t s);
 int force_occupancy(int variant, int *regs, int *threads, int *iblock);   // resident CTAs per SM of the force kernel
-int force_sym_occupancy(int *regs);                                       // same for the two-sided kernel
+int force_sym_occupancy(int rows, int *regs);                             // same for the two-sided kernel (4 or 8 rows per lane)
 constexpr int kForceVariants = 6;
 size_t fpart_slabs(int force_grid, int shard_cap, int iblock);   // slabs of `iblock` float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)

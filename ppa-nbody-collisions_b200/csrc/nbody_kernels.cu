@@ -672,21 +672,20 @@ __host__ __device__ inline int sym_block_index(int X, int Y, int Q)
 #define NB_SYM_UNROLL 32
 #endif
 constexpr int kSymUnroll = NB_SYM_UNROLL;   // sub-steps per iteration of the ring loop
-constexpr int kSymIPT = 4;
 constexpr int kSymThreads = 256;
 constexpr int kSymDynSmem = kStages * kSortedTileFloats * 4;
 
-template <bool TEST>
+template <bool TEST, int IPT>
 __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
-                                             const float (&nx)[kSymIPT], const float (&ny)[kSymIPT],
-                                             const float (&nm)[kSymIPT], const float (&thr)[kSymIPT], const float2 s2,
-                                             float2 (&tfx)[kSymIPT], float2 (&tfy)[kSymIPT], bool &cand, const int lane)
+                                             const float (&nx)[IPT], const float (&ny)[IPT],
+                                             const float (&nm)[IPT], const float (&thr)[IPT], const float2 s2,
+                                             float2 (&tfx)[IPT], float2 (&tfy)[IPT], bool &cand, const int lane)
 {
     const int src = (lane + 1) & 31;
 #pragma unroll kSymUnroll
     for (int s = 0; s < 32; ++s) {
 #pragma unroll
-        for (int q = 0; q < kSymIPT; ++q) {
+        for (int q = 0; q < IPT; ++q) {
             const float2 dx = __fadd2_rn(xs, make_float2(nx[q], nx[q]));
             const float2 dy = __fadd2_rn(ys, make_float2(ny[q], ny[q]));
             const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, s2));
@@ -739,18 +738,19 @@ __device__ __forceinline__ void push_candidate(const DevState &st, const int ran
 // One round redone with the reference predicate (src/nbody.cu:126-134): pairs that hit give no force to either
 // body (:215-226) and become candidates of both rows; `own_tile`: rows and chunk come from the same tile, every
 // ordered pair is met there on its own, so only the row side counts and the self pair is skipped.
+template <int IPT>
 __device__ __noinline__ void sym_exact_round(const DevState &st, const float *tl, const float *rows, const int c,
                                              const int k, const bool own_tile, const float soft2, const int rank,
                                              float4 (*acc_s)[kSymThreads], float4 *gacc)
 {
     const int lane = threadIdx.x & 31;
     const int src = (lane + 1) & 31;
-    float xi[kSymIPT], yi[kSymIPT], mi[kSymIPT], ri[kSymIPT];
-    float2 tfx[kSymIPT], tfy[kSymIPT];
-    int oi[kSymIPT];
+    float xi[IPT], yi[IPT], mi[IPT], ri[IPT];
+    float2 tfx[IPT], tfy[IPT];
+    int oi[IPT];
 #pragma unroll
-    for (int q = 0; q < kSymIPT; ++q) {
-        const int rs = 128 * k + 32 * q + lane;
+    for (int q = 0; q < IPT; ++q) {
+        const int rs = 32 * IPT * k + 32 * q + lane;
         xi[q] = rows[rs];
         yi[q] = rows[kTJ + rs];
         mi[q] = rows[2 * kTJ + rs];
@@ -774,8 +774,8 @@ __device__ __noinline__ void sym_exact_round(const DevState &st, const float *tl
             const int oj = __float_as_int(tl[4 * kTJ + js]);
             float gxe = 0.f, gye = 0.f;
 #pragma unroll
-            for (int q = 0; q < kSymIPT; ++q) {
-                const bool valid = (oi[q] >= 0) & (oj >= 0) & !(own_tile & (js == 128 * k + 32 * q + lane));
+            for (int q = 0; q < IPT; ++q) {
+                const bool valid = (oi[q] >= 0) & (oj >= 0) & !(own_tile & (js == 32 * IPT * k + 32 * q + lane));
                 const float dx = xj - xi[q], dy = yj - yi[q];
                 const float d2 = fmaf(dx, dx, dy * dy);
                 const float rs = ri[q] + rj;
@@ -818,7 +818,7 @@ __device__ __noinline__ void sym_exact_round(const DevState &st, const float *tl
         gy.y = __shfl_sync(0xffffffffu, gy.y, src);
     }
 #pragma unroll
-    for (int q = 0; q < kSymIPT; ++q) {
+    for (int q = 0; q < IPT; ++q) {
         float4 a = acc_s[q][threadIdx.x];
         two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
         two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
@@ -834,17 +834,22 @@ __device__ __noinline__ void sym_exact_round(const DevState &st, const float *tl
     }
 }
 
-__global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevState st, const StepParams p)
+template <int IPT, int MINB>
+__global__ void __launch_bounds__(kSymThreads, MINB) force_sym_kernel(const DevState st, const StepParams p)
 {
     extern __shared__ __align__(128) float tiles_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ float4 acc_s[kSymIPT][kSymThreads];        // per thread and row {fx_hi, fx_lo, fy_hi, fy_lo}
+    __shared__ float4 acc_s[IPT][kSymThreads];        // per thread and row {fx_hi, fx_lo, fy_hi, fy_lo}
     __shared__ float4 gacc[2][kTJ / 2];                   // per j pair {gx0, gx1, gy0, gy1}, double-buffered over tile pairs
     __shared__ int s_rc[2];
     if (!st.desc->sym) return;
     float(*tiles)[kSortedTileFloats] = reinterpret_cast<float(*)[kSortedTileFloats]>(tiles_dyn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = warp >> 1, h = warp & 1;        // row group (128 rows), half of the J tile
+    // 512 rows = GROUPS row groups of 32 IPT rows; the HSPLIT warps of a group share its rows and split the 8 chunks
+    // of a J tile: ROUNDS chunks each, one per round
+    constexpr int GROUPS = kTJ / (32 * IPT), HSPLIT = 8 / GROUPS, ROUNDS = 8 / HSPLIT;
+    static_assert(GROUPS * HSPLIT == 8 && ROUNDS == GROUPS, "8 warps, all on different chunks in every round");
+    const int k = warp / HSPLIT, h = warp % HSPLIT;
     const int T = st.desc->n_jtiles, S = st.desc->sym_S, Q = st.desc->sym_Q;
     const int nblk = st.desc->sym_blocks;
     const float rmax = st.desc->rmax;
@@ -904,10 +909,10 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
 #pragma unroll 1
         for (int I = I0; I < I1; ++I) {
             const float *rows = st.jts + (size_t)I * kSortedTileFloats;
-            float nx[kSymIPT], ny[kSymIPT], nm[kSymIPT], thr[kSymIPT];
+            float nx[IPT], ny[IPT], nm[IPT], thr[IPT];
 #pragma unroll
-            for (int q = 0; q < kSymIPT; ++q) {
-                const int rs = 128 * k + 32 * q + lane;
+            for (int q = 0; q < IPT; ++q) {
+                const int rs = 32 * IPT * k + 32 * q + lane;
                 nx[q] = -rows[rs];
                 ny[q] = -rows[kTJ + rs];
                 nm[q] = -rows[2 * kTJ + rs];
@@ -918,15 +923,15 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             }
             // row-side sums of the rounds since the last fold (registers); banked in the compensated shared
             // accumulators before every pre-tested round and at the end of every tile pair
-            float2 tfx[kSymIPT], tfy[kSymIPT];
+            float2 tfx[IPT], tfy[IPT];
 #pragma unroll
-            for (int q = 0; q < kSymIPT; ++q) {
+            for (int q = 0; q < IPT; ++q) {
                 tfx[q] = make_float2(0.f, 0.f);
                 tfy[q] = make_float2(0.f, 0.f);
             }
             auto fold_rows = [&]() {
 #pragma unroll
-                for (int q = 0; q < kSymIPT; ++q) {
+                for (int q = 0; q < IPT; ++q) {
                     float4 a = acc_s[q][tid];
                     two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
                     two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
@@ -938,8 +943,13 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             float4 rb;                            // bounding box of this warp's 128 rows
             {
                 const float4 *bx = reinterpret_cast<const float4 *>(rows + 5 * kTJ);
-                const float4 a = bx[2 * k], b = bx[2 * k + 1];
-                rb = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+                constexpr int BOXES = 32 * IPT / kSubPart;        // 64-body boxes per row group
+                rb = bx[BOXES * k];
+#pragma unroll
+                for (int e = 1; e < BOXES; ++e) {
+                    const float4 b = bx[BOXES * k + e];
+                    rb = make_float4(fminf(rb.x, b.x), fminf(rb.y, b.y), fmaxf(rb.z, b.z), fmaxf(rb.w, b.w));
+                }
             }
 #pragma unroll 1
             for (int J = diag ? I : J0; J < J1; ++J, ++it) {
@@ -949,8 +959,8 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
                 const bool own = J == I;
                 const int buf = (int)(it & 1u);
 #pragma unroll 1
-                for (int r = 0; r < 4; ++r) {
-                    const int c = 4 * h + ((k + r) & 3);
+                for (int r = 0; r < ROUNDS; ++r) {
+                    const int c = ROUNDS * h + ((k + r) % ROUNDS);
                     const float4 cb = reinterpret_cast<const float4 *>(tl + 5 * kTJ)[c];
                     const bool may_hit = !((cb.x - rb.z > Rb) | (rb.x - cb.z > Rb) | (cb.y - rb.w > Rb) | (rb.y - cb.w > Rb));
                     float2 xs = *reinterpret_cast<const float2 *>(tl + 64 * c + 2 * lane);
@@ -962,17 +972,17 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
                         // the round's row sums must be separable (they are dropped if the pre-test fires):
                         // bank what earlier rounds left in the registers first
                         fold_rows();
-                        sym_substeps<true>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
+                        sym_substeps<true, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
                     } else {
-                        sym_substeps<false>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
+                        sym_substeps<false, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
                         ++n_culled;
                     }
                     if (may_hit && __any_sync(0xffffffffu, cand)) {
                         // rare: a possible hit somewhere in the round; its sums are dropped and the round redone
-                        sym_exact_round(st, tl, rows, c, k, own, p.soft2, p.rank, acc_s, gacc[buf]);
+                        sym_exact_round<IPT>(st, tl, rows, c, k, own, p.soft2, p.rank, acc_s, gacc[buf]);
                         n_exact += 2;
 #pragma unroll
-                        for (int q = 0; q < kSymIPT; ++q) {
+                        for (int q = 0; q < IPT; ++q) {
                             tfx[q] = make_float2(0.f, 0.f);
                             tfy[q] = make_float2(0.f, 0.f);
                         }
@@ -1010,14 +1020,19 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             // i side of the finished row of tile pairs: the two warps that share these rows, in fixed order
             __syncthreads();
             if (h == 0) {
-                float2 *dst = st.part + (size_t)C * stride + (size_t)I * kTJ + 128 * k + lane;
+                float2 *dst = st.part + (size_t)C * stride + (size_t)I * kTJ + 32 * IPT * k + lane;
 #pragma unroll
-                for (int q = 0; q < kSymIPT; ++q) {
+                for (int q = 0; q < IPT; ++q) {
                     float4 a = acc_s[q][tid];
-                    const float4 b = acc_s[q][tid + 32];
-                    two_sum(a.x, a.y, b.x);
-                    two_sum(a.z, a.w, b.z);
-                    float2 v = make_float2(a.x + (a.y + b.y), a.z + (a.w + b.w));
+#pragma unroll
+                    for (int e = 1; e < HSPLIT; ++e) {
+                        const float4 b = acc_s[q][tid + 32 * e];
+                        two_sum(a.x, a.y, b.x);
+                        two_sum(a.z, a.w, b.z);
+                        a.y += b.y;
+                        a.w += b.w;
+                    }
+                    float2 v = make_float2(a.x + a.y, a.z + a.w);
                     if (diag && I != I0) {        // the diagonal block's rows already hold j-side sums of earlier tiles
                         const float2 o = dst[32 * q];
                         v = make_float2(o.x + v.x, o.y + v.y);
@@ -1029,7 +1044,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         }
     }
     if (p.count_stats && lane == 0) {
-        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)it * 8ull);        // 4 rounds x 2 sub-chunks of 32 bodies
+        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)it * (2ull * ROUNDS));   // rounds x 2 sub-chunks of 32 bodies
         atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_exact);
         atomicAdd(&st.ctr->culled_parts, (unsigned long long)n_culled);
     }
@@ -1532,7 +1547,10 @@ cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !p.sym || p.sort_min_n <= 0) return e;
     // sort-capable step: whichever kernel the step descriptor does not name returns at once
-    force_sym_kernel<<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
+    if (p.sym_rows == 8)
+        force_sym_kernel<8, 2><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
+    else
+        force_sym_kernel<4, 3><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
     return cudaGetLastError();
 }
 
@@ -1622,13 +1640,19 @@ int force_occupancy(int variant, int *regs, int *threads, int *iblock)
     return occ;
 }
 
-int force_sym_occupancy(int *regs)
+int force_sym_occupancy(int rows, int *regs)
 {
     int occ = 0;
     cudaFuncAttributes fa = {};
-    cudaFuncSetAttribute(force_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel, kSymThreads, kSymDynSmem);
-    cudaFuncGetAttributes(&fa, force_sym_kernel);
+    if (rows == 8) {
+        cudaFuncSetAttribute(force_sym_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel<8, 2>, kSymThreads, kSymDynSmem);
+        cudaFuncGetAttributes(&fa, force_sym_kernel<8, 2>);
+    } else {
+        cudaFuncSetAttribute(force_sym_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel<4, 3>, kSymThreads, kSymDynSmem);
+        cudaFuncGetAttributes(&fa, force_sym_kernel<4, 3>);
+    }
     if (regs) *regs = fa.numRegs;
     return occ;
 }

@@ -13,12 +13,13 @@ import __graft_entry__ as G  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 nb = G.load_package()
+EXTRA = int(__import__("os").environ.get("NB_EXTRA_FLAGS", "0"))      # e.g. 128 = NB_FLAG_SYM_ROWS8 (experimental variant)
 
 
 def parity(n, field, steps=4, softening=0.0):
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
     sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, event_capacity=64 * n,
-                        sort_min_n=1, flags=nb.FLAG_PAIR_HALVING, softening=softening)
+                        sort_min_n=1, flags=nb.FLAG_PAIR_HALVING | EXTRA, softening=softening)
     sim.upload(block0, n)
     cpu, n_cpu = block0.copy(), n
     par = O.params(field_w=field, field_h=field, coverage=O.COVERAGE_FULL, softening=softening)
@@ -54,7 +55,7 @@ for n in [int(a) for a in sys.argv[1:]] or [131072, 1048576]:
     field = int(R)
     block0 = nb.generate(nb.SCENARIO_DISC, n, extent=R, field_w=field, field_h=field)
     outs = {}
-    for name, flags in (("one_sided", 0), ("two_sided", nb.FLAG_PAIR_HALVING), ("two_sided_again", nb.FLAG_PAIR_HALVING)):
+    for name, flags in (("one_sided", nb.FLAG_ONE_SIDED), ("two_sided", nb.FLAG_PAIR_HALVING | EXTRA), ("two_sided_again", nb.FLAG_PAIR_HALVING | EXTRA)):
         sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, flags=flags, event_capacity=1 << 20)
         sim.upload(block0, n)
         sim.step(3)
