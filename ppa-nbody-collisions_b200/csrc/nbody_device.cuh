@@ -172,6 +172,7 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
+cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream_t s);    // nbody_sym.cu
 cudaError_t launch_sym_reduce(const DevState &st, const StepParams &p, cudaStream_t s);   // sharded two-sided kernel: before ...
 cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s);    // ... and after the allgather of xbuf
 cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s);
