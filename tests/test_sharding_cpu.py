@@ -1,4 +1,5 @@
-"""The N > 1 path on the CPU: world_size-2 and -3 `gloo` runs of the host-side sharding logic.
+"""The N > 1 path on the CPU: world_size-2 and -3 `gloo` runs of the host-side sharding logic (row shards of the
+one-sided steps; at the end of the file the block deal and the exchange of the two-sided steps).
 
 Each rank owns the i-block-aligned row range the library's own plan (nb_plan_host, the code the device
 runs at the end of every step) assigns it, evaluates only those rows (oracle.rows stands in for the force +
@@ -147,3 +148,93 @@ def test_two_sided_plan_flags(nb):
     assert nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["sorted"] == 0
     with pytest.raises(nb.NbodyError):
         nb.plan_block(4, 10)
+
+
+def _pair_block(x, y, m, r, rows, cols, own):
+    """Two-sided evaluation of the tile pair rows x cols the way force_sym_kernel defines it: float32 predicate with the
+    reference's roundings (d2 = fma(dx, dx, dy * dy) <= (r_i + r_j)^2), hit pairs excluded from the force on BOTH bodies
+    and reported for both rows; own tile: every ordered pair is met on its own, self pair skipped."""
+    xi, yi, xj, yj = x[rows, None], y[rows, None], x[None, cols], y[None, cols]
+    dx = (xj - xi).astype(np.float32)
+    dy = (yj - yi).astype(np.float32)
+    dy2 = (dy * dy).astype(np.float32)
+    d2 = (dx.astype(np.float64) * dx.astype(np.float64) + dy2.astype(np.float64)).astype(np.float32)     # fmaf
+    rs = (r[rows, None] + r[None, cols]).astype(np.float32)
+    hit = d2 <= (rs * rs).astype(np.float32)
+    valid = np.ones_like(hit)
+    if own:
+        valid &= rows[:, None] != cols[None, :]
+    w = np.where(valid & ~hit, np.maximum(d2.astype(np.float64), 1.0) ** -1.5, 0.0)     # non-hit pairs are >= 100 apart
+    fi = np.stack([(w * dx * m[None, cols]).sum(axis=1), (w * dy * m[None, cols]).sum(axis=1)], axis=1)
+    fj = np.stack([-(w * dx * m[rows, None]).sum(axis=0), -(w * dy * m[rows, None]).sum(axis=0)], axis=1)
+    ii, jj = np.nonzero(valid & hit)
+    pairs = [(int(rows[a]), int(cols[b])) for a, b in zip(ii, jj)]
+    if not own:
+        pairs += [(b, a) for a, b in pairs]
+    return fi, (None if own else fj), pairs
+
+
+def _two_sided_worker(rank: int, world: int, port: int, n: int, field: int, out_dir: str):
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    nb = G.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    block = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    pos, _, m, r = nb.split(block, n)
+    x, y = pos[:, 0].copy(), pos[:, 1].copy()
+    plan = nb.plan(n, rank=rank, world=world, sort_min_n=1024)          # the library's own cut of the pair triangle
+    assert plan["two_sided"] == 1
+    S, Q, T = plan["sym_S"], plan["sym_Q"], plan["n_jtiles"]
+    F = np.zeros((n, 2))
+    pairs = []
+    tile = lambda t: np.arange(t * 512, min((t + 1) * 512, n))
+    for b in range(rank, plan["sym_blocks"], world):                     # rank r takes blocks r, r + W, ...
+        R, C = nb.plan_block(Q, b)
+        for I in range(R * S, min((R + 1) * S, T)):
+            for J in range(I if R == C else C * S, min((C + 1) * S, T)):
+                fi, fj, pp = _pair_block(x, y, m, r, tile(I), tile(J), own=(I == J))
+                F[tile(I)] += fi
+                if fj is not None:
+                    F[tile(J)] += fj
+                pairs += pp
+    # the exchange: one all_gather of {partial forces, count, pairs} per rank
+    cap = 4 * n
+    mine = np.full((cap, 2), -1, dtype=np.int64)
+    mine[:len(pairs)] = np.array(pairs, dtype=np.int64).reshape(-1, 2)
+    Fs = [torch.zeros(n, 2, dtype=torch.float64) for _ in range(world)]
+    Ps = [torch.zeros(cap, 2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(Fs, torch.from_numpy(F))
+    dist.all_gather(Ps, torch.from_numpy(mine))
+    total = sum(f.numpy() for f in Fs)                                   # rank order, identical on every rank
+    allp = np.concatenate([p.numpy() for p in Ps])
+    allp = allp[allp[:, 0] >= 0]
+    np.savez(os.path.join(out_dir, f"two_sided_{rank}.npz"), F=total, pairs=allp[np.lexsort((allp[:, 1], allp[:, 0]))])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,field", [(2, 1500, 6000), (3, 2600, 9000), (2, 3000, 6000)])
+def test_two_sided_deal_and_exchange_equal_the_one_sided_sum(oracle, nb, tmp_path, world, n, field):
+    """world_size-2 / -3 gloo run of the sharded two-sided flow: blocks of the pair triangle dealt round-robin by the
+    library's plan, every rank's partial forces and hit pairs brought together by one all_gather.  The sum must be the
+    all-pairs force on every body and the union of the pairs the oracle's event list, on every rank."""
+    import torch.multiprocessing as mp
+    mp.spawn(_two_sided_worker, args=(world, _free_port(), n, field, str(tmp_path)), nprocs=world, join=True)
+    block = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    pos, _, m, r = nb.split(block, n)
+    x, y = pos[:, 0].copy(), pos[:, 1].copy()
+    everyone = np.arange(n)
+    want_F, _, want_pairs = _pair_block(x, y, m, r, everyone, everyone, own=True)
+    want_pairs = np.array(sorted(want_pairs), dtype=np.int64).reshape(-1, 2)
+    par = oracle.params(field_w=field, field_h=field, coverage=oracle.COVERAGE_FULL)
+    _, _, ev = oracle.step(block.copy(), n, par, want_events=True)
+    ev_pairs = np.array(sorted(zip(ev["i"].tolist(), ev["j"].tolist())), dtype=np.int64).reshape(-1, 2)
+    assert len(ev_pairs) > 0 and np.array_equal(want_pairs, ev_pairs), "numpy restatement of the predicate differs from the oracle"
+    outs = [np.load(tmp_path / f"two_sided_{k}.npz") for k in range(world)]
+    for o in outs:
+        assert np.array_equal(o["pairs"], ev_pairs)
+        assert np.array_equal(o["F"], outs[0]["F"]), "ranks disagree on the summed forces"
+        assert np.abs(o["F"] - want_F).max() <= 1e-9 * np.abs(want_F).max()
