@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NB_VERSION 100
+#define NB_VERSION 101   /* 101: nb_stats and nb_plan grew (two-sided force kernel), nb_plan_block*, new flags */
 
 /* error codes */
 #define NB_OK 0
