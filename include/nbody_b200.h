@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NB_VERSION 101   /* 101: nb_stats and nb_plan grew (two-sided force kernel), nb_plan_block*, new flags */
+#define NB_VERSION 102   /* 102: nb_stats.kernel_launches, nb_probe_fp32; 101: nb_stats / nb_plan grew (two-sided kernel) */
 
 /* error codes */
 #define NB_OK 0
@@ -128,6 +128,11 @@ typedef struct nb_stats {
     int64_t culled_parts;     /* j parts that ran without the collision pre-test (sorted stream)    */
     int32_t pair_halving;     /* 1: the next step will run the two-sided force kernel               */
     int32_t sym_regs;         /* registers per thread of the two-sided force kernel (0: not in use) */
+    int64_t kernel_launches;  /* kernels of this library executed for this context since nb_create: direct launches
+                                 plus the kernel nodes of every graph replay (counted at the launch sites, NCCL's
+                                 own kernels not included)                                                         */
+    int32_t force_partials;   /* 8-byte partial force sums per body the finish kernel adds up in the next step     */
+    int32_t reserved;
 } nb_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -205,6 +210,13 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out);
    nb_plan_block_index is its inverse (any order of the two super-tiles).  Host only. */
 int nb_plan_block(int Q, int b, int *R, int *C);
 int nb_plan_block_index(int Q, int X, int Y);
+
+/* ---- measurement ---------------------------------------------------------- */
+/*
+ * FP32 peak of `device` measured now: a stream of independent packed fma.rn.f32x2, 32 warps per SM, no memory
+ * traffic (about 5 ms).  The denominator of the force kernels' roofline in bench.py.
+ */
+int nb_probe_fp32(int device, double *tflops);
 
 /* ---- render (src/nbody.cu:294-348, 350-371) ------------------------------ */
 /* Rasterise the current bodies into a w*h 8-bit image (background 254, body 0). */

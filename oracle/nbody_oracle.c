@@ -130,6 +130,36 @@ void orc_init_square(float *block, int n, uint64_t seed, int field_w, int field_
     }
 }
 
+/*
+ * Synthetic scenarios of BASELINE.json configs[1..4] (the reference itself only generates the
+ * square above, src/nbody.cu:401-416).  Restated here so that the checkers and bench.py's reference arm can
+ * build their inputs WITHOUT loading the product library; tests/test_oracle_golden.py checks bit equality
+ * with the product's nb_generate.  Per body four draws in the reference's order (u1, u2, m, r), positions
+ * from (radius^2 fraction, angle) in double, stored as float; solid-body spin omega about the disc centre.
+ */
+void orc_init_disc_part(float *block, int n, int first, int count, uint64_t seed, double cx, double cy, double R,
+                        double bulk_vx, double bulk_vy, double omega,
+                        float min_mass, float max_mass, float min_radius, float max_radius)
+{
+    float *pos = block, *vel = block + 2 * (size_t)n;
+    float *mass = block + 4 * (size_t)n, *rad = block + 5 * (size_t)n;
+    const double two_pi = 6.283185307179586476925286766559;
+    orc_rng g;
+    orc_rng_seed(&g, seed);
+    for (int k = 0; k < count; ++k) {
+        const int b = first + k;
+        const double u1 = orc_rng_fval(&g), u2 = orc_rng_fval(&g);
+        const double rr = R * sqrt(u1), th = two_pi * u2;
+        const double x = rr * cos(th), y = rr * sin(th);
+        pos[2 * b] = (float)(cx + x);
+        pos[2 * b + 1] = (float)(cy + y);
+        vel[2 * b] = (float)(bulk_vx - omega * y);
+        vel[2 * b + 1] = (float)(bulk_vy + omega * x);
+        mass[b] = (float)orc_rng_fval_range(&g, min_mass, max_mass);
+        rad[b] = (float)orc_rng_fval_range(&g, min_radius, max_radius);
+    }
+}
+
 /* ---------------------------------------------------------------------- */
 /* Coverage: which threads exist and how long the last j-tile is.          */
 /* ---------------------------------------------------------------------- */

@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.orc_rng_fval.restype = C.c_double
         L.orc_init_square.argtypes = [fp, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_float, C.c_float]
+        L.orc_init_disc_part.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_uint64] + [C.c_double] * 6 + [C.c_float] * 4
         L.orc_coverage.argtypes = [C.c_int, C.c_int, C.POINTER(OrcCov)]
         L.orc_rows.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
                                fp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
@@ -121,6 +122,24 @@ def init_square(n, seed=1024, field_w=100000, field_h=100000, min_mass=1e4, max_
     lib().orc_init_square(_fptr(block), n, seed, field_w, field_h,
                           np.float32(min_mass), np.float32(max_mass),
                           np.float32(min_radius), np.float32(max_radius))
+    return block
+
+
+def init_disc(n, extent, seed=1024, min_mass=1e4, max_mass=1e17, min_radius=50.0, max_radius=200.0) -> np.ndarray:
+    """Uniform disc of radius `extent`, v = 0 (BASELINE configs[1..3]); bit-equal to the product's nb_generate."""
+    block = np.zeros(6 * n, dtype=np.float32)
+    lib().orc_init_disc_part(_fptr(block), n, 0, n, seed, 0.0, 0.0, float(extent), 0.0, 0.0, 0.0,
+                             np.float32(min_mass), np.float32(max_mass), np.float32(min_radius), np.float32(max_radius))
+    return block
+
+
+def init_two_galaxy(n, extent, seed=1024, min_mass=1e4, max_mass=1e17, min_radius=50.0, max_radius=200.0) -> np.ndarray:
+    """Two counter-rotating discs on an encounter course (BASELINE configs[4]); bit-equal to nb_generate."""
+    block = np.zeros(6 * n, dtype=np.float32)
+    R, n0 = float(extent), n // 2
+    mr = (np.float32(min_mass), np.float32(max_mass), np.float32(min_radius), np.float32(max_radius))
+    lib().orc_init_disc_part(_fptr(block), n, 0, n0, seed, -1.5 * R, -0.25 * R, R, 400.0, 0.0, 2.0e-4, *mr)
+    lib().orc_init_disc_part(_fptr(block), n, n0, n - n0, seed + 1, 1.5 * R, 0.25 * R, R, -400.0, 0.0, -2.0e-4, *mr)
     return block
 
 

@@ -35,7 +35,7 @@ SYMBOLS = [
     "nb_create", "nb_destroy", "nb_last_error", "nb_version", "nb_upload", "nb_download", "nb_num_bodies",
     "nb_step", "nb_step_timed", "nb_step_profile", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_render", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
-    "nb_rng_fval_range", "nb_generate",
+    "nb_rng_fval_range", "nb_generate", "nb_probe_fp32",
 ]
 
 
@@ -57,7 +57,8 @@ class Stats(C.Structure):
                 ("sm_count", C.c_int32), ("force_grid", C.c_int32), ("force_regs", C.c_int32),
                 ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("force_threads", C.c_int32),
                 ("force_variant", C.c_int32), ("culled_parts", C.c_int64),
-                ("pair_halving", C.c_int32), ("sym_regs", C.c_int32)]
+                ("pair_halving", C.c_int32), ("sym_regs", C.c_int32), ("kernel_launches", C.c_int64),
+                ("force_partials", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Plan(C.Structure):
@@ -146,6 +147,7 @@ def lib() -> C.CDLL:
     L.nb_rng_fval_range.argtypes = [C.POINTER(Rng), C.c_double, C.c_double]
     L.nb_rng_fval_range.restype = C.c_double
     L.nb_generate.argtypes = [C.POINTER(Scenario), vp]
+    L.nb_probe_fp32.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -297,6 +299,15 @@ class Simulation:
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)
         self._check("nb_comm_init", lib().nb_comm_init(self._h, buf))
+
+
+def probe_fp32(device: int = 0) -> float:
+    """Measured FP32 peak of the device in TFLOP/s (packed FFMA2 stream), see nb_probe_fp32."""
+    t = C.c_double(0)
+    rc = lib().nb_probe_fp32(device, C.byref(t))
+    if rc != OK:
+        raise NbodyError("nb_probe_fp32", rc, "no usable CUDA device")
+    return t.value
 
 
 def comm_unique_id() -> bytes:

@@ -47,7 +47,17 @@ struct nb_ctx {
     void *dev_block;                   // staging for upload/download: the BodiesData block, 24 * cap bytes
     unsigned char *dev_img;
     size_t dev_img_bytes;
+    long long launches;                // kernels of this library executed on behalf of this context (direct + graph nodes)
+    long long graph_nodes[2];          // kernel nodes of graph[k]
     char err[512];
+};
+
+// counts the kernels launched directly (not captured) while it is alive
+struct LaunchScope {
+    nb_ctx *c;
+    long long c0;
+    explicit LaunchScope(nb_ctx *ctx) : c(ctx), c0(launch_counter()) {}
+    ~LaunchScope() { c->launches += launch_counter() - c0; }
 };
 
 static char g_create_err[512] = "";
@@ -343,6 +353,7 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
     }
     NB_CUDA(c, cudaSetDevice(c->device));
     NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    LaunchScope scope(c);
     c->ring_pos = 0;
     if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
@@ -405,6 +416,7 @@ int nb_download(nb_ctx *c, void *bodies, int capacity_n, int *n_out)
         set_err(c, "nb_download: host buffer holds %d bodies, %d are live", capacity_n, d.n);
         return NB_ERR_CAPACITY;
     }
+    LaunchScope scope(c);
     if (d.n > 0) {
         NB_CUDA(c, launch_export(c->st, (float *)c->dev_block, d.n, c->stream));
         NB_CUDA(c, cudaMemcpyAsync(bodies, c->dev_block, (size_t)24 * d.n, cudaMemcpyDeviceToHost, c->stream));
@@ -448,7 +460,10 @@ static int ensure_graph(nb_ctx *c, int which)
     if (c->graph_ready[which]) return NB_OK;
     cudaGraph_t g = nullptr;
     NB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const long long c0 = launch_counter();
     int rc = enqueue_step(c, which ? c->sp : c->sp_plain, nullptr, nullptr);
+    c->graph_nodes[which] = launch_counter() - c0;      // recorded, not executed: they count once per replay
+    launch_counter() = c0;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     if (rc != NB_OK) {
         if (g) cudaGraphDestroy(g);
@@ -471,10 +486,17 @@ static int ensure_graph(nb_ctx *c, int which)
 static int run_steps(nb_ctx *c, int n_steps)
 {
     int rc;
+    LaunchScope scope(c);
     const bool sortable = c->sp.sort_min_n > 0;
     for (int s = 0; s < n_steps; ++s) {
         int which = 0;
-        if (sortable) {
+        if (sortable && c->sp.world > 1) {
+            // sharded: the two graphs hold different collectives (graph[1] also gathers xbuf), so the choice must be
+            // the same on every rank and cannot depend on how far each host has read ahead of its device.  Always
+            // replay the rich graph: its sort / two-sided kernels exit at once when the step descriptor (identical
+            // on every rank) does not name them.
+            which = 1;
+        } else if (sortable) {
             cudaEvent_t &slot = c->ring[c->ring_pos % 16];
             if (c->ring_pos >= 16) NB_CUDA(c, cudaEventSynchronize(slot));
             which = *c->host_n >= c->sp.sort_min_n ? 1 : 0;
@@ -484,8 +506,9 @@ static int run_steps(nb_ctx *c, int n_steps)
         } else {
             if ((rc = ensure_graph(c, which)) != NB_OK) return rc;
             NB_CUDA(c, cudaGraphLaunch(c->graph[which], c->stream));
+            c->launches += c->graph_nodes[which];
         }
-        if (sortable) {
+        if (sortable && c->sp.world <= 1) {
             NB_CUDA(c, cudaEventRecord(c->ring[c->ring_pos % 16], c->stream));
             ++c->ring_pos;
         }
@@ -533,6 +556,7 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
         c->fev.push_back(e);
     }
     NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    LaunchScope scope(c);
     for (int s = 0; s < n_steps; ++s)
         if ((rc = enqueue_step(c, c->sp, c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
     NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -559,6 +583,7 @@ int nb_step_profile(nb_ctx *c, int n_steps, float ms[5])
         c->fev.push_back(e);
     }
     for (int k = 0; k < 5; ++k) ms[k] = 0.f;
+    LaunchScope scope(c);
     for (int s = 0; s < n_steps; ++s) {
         if ((rc = enqueue_step(c, c->sp, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
         NB_CUDA(c, cudaEventSynchronize(c->fev[5]));
@@ -597,6 +622,8 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->sym_regs = c->sp.sym ? c->sym_regs : 0;
     out->row_lo = d.row_lo;
     out->row_hi = d.row_hi;
+    out->kernel_launches = c->launches;
+    out->force_partials = d.sym ? (c->sp.world > 1 ? c->sp.world : d.sym_Q) : 1;
     return NB_OK;
 }
 
@@ -689,6 +716,7 @@ int nb_render(nb_ctx *c, uint8_t *image, int w, int h)
         NB_CUDA(c, cudaMalloc((void **)&c->dev_img, bytes));
         c->dev_img_bytes = bytes;
     }
+    LaunchScope scope(c);
     NB_CUDA(c, cudaMemsetAsync(c->dev_img, 254, bytes, c->stream));      // src/nbody.cu:534
     NB_CUDA(c, launch_render(c->st, d.n, c->dev_img, w, h, c->sp.field_w, c->sp.field_h, c->stream));
     NB_CUDA(c, cudaMemcpyAsync(image, c->dev_img, bytes, cudaMemcpyDeviceToHost, c->stream));

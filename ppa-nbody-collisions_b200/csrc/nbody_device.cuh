@@ -168,6 +168,11 @@ __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
     return reinterpret_cast<float2 *>(st.post + (size_t)rank * st.shard_cap * 24 + (size_t)st.shard_cap * 16);
 }
 
+// Kernels this library itself has launched (or recorded into a graph being captured) on the calling thread: every
+// launch site bumps it, the C ABI turns it into nb_stats.kernel_launches (a count, not a formula).
+long long &launch_counter();
+inline void count_launch(int k = 1) { launch_counter() += k; }
+
 // kernels (nbody_kernels.cu)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);

@@ -989,9 +989,16 @@ constexpr int kForceDynSmem = kStages * kSortedTileFloats * 4;
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+long long &launch_counter()
+{
+    static thread_local long long n = 0;
+    return n;
+}
+
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s)
 {
     plan_kernel<<<1, 32, 0, s>>>(st, p, n);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1001,6 +1008,7 @@ cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, c
 #define X(ID, PK, W, I, MB)                                                                    \
     case ID:                                                                                   \
         force_kernel<PK, W, I, MB><<<p.force_grid, W * 32, kForceDynSmem, s>>>(st, p);         \
+        count_launch();                                                                        \
         break;
         NB_FORCE_VARIANTS(X)
 #undef X
@@ -1017,6 +1025,7 @@ cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t 
 {
     const int grid = (st.shard_cap + 255) / 256;
     finish_kernel<<<grid, 256, 0, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1025,10 +1034,12 @@ cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount
     const int grid = (st.cap + kCompactTile - 1) / kCompactTile;
     if (p.world > 1 || recount) {            // rows finished on other GPUs, or removed after finish (merge): count now
         count_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
+        count_launch();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     scatter_kernel<<<grid, kCompactThreads, 0, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1036,7 +1047,9 @@ cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s
 {
     const int grid = (st.cap + 255) / 256;
     merge_link_kernel<<<grid, 256, 0, s>>>(st);
+    count_launch();
     merge_apply_kernel<<<grid, 256, 0, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1044,6 +1057,7 @@ cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStr
 {
     const int span = st.cap + kTJ;
     ingest_kernel<<<(span + 255) / 256, 256, 0, s>>>(st, block, n);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1051,6 +1065,7 @@ cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t 
 {
     if (n <= 0) return cudaSuccess;
     export_kernel<<<(n + 255) / 256, 256, 0, s>>>(st, block, n);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -1059,6 +1074,7 @@ cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, 
 {
     if (n <= 0) return cudaSuccess;
     render_kernel<<<(n + 127) / 128, 128, 0, s>>>(st, n, img, w, h, field_w, field_h);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -216,12 +216,17 @@ cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s)
     const int per_block = sort_per_block(st.cap);
     const int nblocks = (st.cap + per_block - 1) / per_block;
     keys_kernel<<<(st.cap + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s>>>(st, p);
+    count_launch();
     for (int pass = 0; pass < 2; ++pass) {
         radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+        count_launch();
         radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
+        count_launch();
         radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+        count_launch();
     }
     gather_kernel<<<(st.cap + kTJ - 1) / kTJ, kTJ, 0, s>>>(st);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -495,18 +495,21 @@ cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream
         force_sym_kernel<8, 2><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
     else
         force_sym_kernel<4, 3><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_sym_reduce(const DevState &st, const StepParams &p, cudaStream_t s)
 {
     sym_reduce_kernel<<<(st.cap + 255) / 256, 256, 0, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s)
 {
     sym_chain_kernel<<<296, 256, 0, s>>>(st, p);
+    count_launch();
     return cudaGetLastError();
 }
 

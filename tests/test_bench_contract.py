@@ -35,6 +35,15 @@ def test_reference_arm_prints_one_json_line():
     cb = out["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and "sample" in cb
     assert "workload" in out["config"]
+    assert out["loads_product_library"] is False, "the reference arm must not map the product's library"
+
+
+def test_reference_arm_takes_every_baseline_config():
+    for name in ("shipped", "disc16k", "cluster"):
+        r = _run("--impl", "reference", "--config", name, "--n", "4096", "--batch", "1", "--steps", "1", "--warmup", "0")
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        assert name in out["config"]["workload"] and out["value"] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():

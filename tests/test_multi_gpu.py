@@ -88,3 +88,111 @@ def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage, sort_m
         ev = ev_all[ev_all["step"] == s]
         ev = ev[np.argsort(ev["i"], kind="stable")]           # each rank's list is sorted; ranks own disjoint row ranges
         assert np.array_equal(ev["i"], ev_cpu["i"]) and np.array_equal(ev["j"], ev_cpu["j"]) and np.array_equal(ev["kind"], ev_cpu["kind"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# The sharded two-sided flow at BASELINE sizes and with several steps per nb_step call (asynchronous path),
+# against the same run on ONE GPU: replicas bit-identical, events / survivors / masses / radii identical to the
+# single-GPU run, velocities within 1e-4 max|v| (force sums differ in rounding only: other summation order).
+# ---------------------------------------------------------------------------------------------------
+def _disc(nb, n):
+    R = 1e5 * np.sqrt(n / 16384.0)               # the shipped scenario's surface density
+    field = int(R)
+    return nb.generate(nb.SCENARIO_DISC, n, extent=R, field_w=field, field_h=field), field
+
+
+def _worker_calls(rank: int, world: int, port: int, n0: int, calls, out_dir: str, sort_min_n: int, flags: int, dense: float):
+    sys.path.insert(0, str(ROOT))
+    import zlib
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    nb = G.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ids = [nb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    block0, field = _disc(nb, n0)
+    if dense != 1.0:                              # crowd the bodies: many die per step (n crosses sort_min_n quickly)
+        block0[:2 * n0] *= np.float32(dense)
+    sim = nb.Simulation(n0, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, device=rank, rank=rank, world=world,
+                        event_capacity=64 * n0, sort_min_n=sort_min_n, flags=flags)
+    sim.comm_init(ids[0])
+    sim.upload(block0, n0)
+    ns = []
+    for k in calls:
+        sim.step(k)                               # k > 1: no host synchronisation between the steps of one call
+        ns.append(sim.num_bodies())
+    got, n = sim.download()
+    ev = sim.events()
+    st = sim.stats()
+    assert st["overflow"] == 0 and st["events_dropped"] == 0
+    np.save(os.path.join(out_dir, f"state_{rank}.npy"), got)
+    np.save(os.path.join(out_dir, f"events_{rank}.npy"), ev)
+    np.save(os.path.join(out_dir, f"ns_{rank}.npy"), np.array(ns))
+    sim.close()
+    dist.destroy_process_group()
+
+
+def _one_gpu(nb, n0, calls, sort_min_n, flags, dense):
+    block0, field = _disc(nb, n0)
+    if dense != 1.0:
+        block0[:2 * n0] *= np.float32(dense)
+    one = nb.Simulation(n0, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, event_capacity=64 * n0,
+                        sort_min_n=sort_min_n, flags=flags)
+    one.upload(block0, n0)
+    ns = []
+    for k in calls:
+        one.step(k)
+        ns.append(one.num_bodies())
+    ref, n_ref = one.download()
+    ev_ref = one.events()
+    one.close()
+    return ref, n_ref, ev_ref, ns
+
+
+def _check_against_one_gpu(nb, tmp_path, world, n0, calls, sort_min_n, flags, dense):
+    ref, n_ref, ev_ref, ns_ref = _one_gpu(nb, n0, calls, sort_min_n, flags, dense)
+    states = [np.load(tmp_path / f"state_{r}.npy") for r in range(world)]
+    for r in range(1, world):
+        assert np.array_equal(states[0].view(np.uint32), states[r].view(np.uint32)), f"replica {r} differs from replica 0"
+    for r in range(world):
+        assert list(np.load(tmp_path / f"ns_{r}.npy")) == ns_ref, f"rank {r}: body counts per call"
+    assert len(states[0]) == 6 * n_ref
+    evs = np.concatenate([np.load(tmp_path / f"events_{r}.npy") for r in range(world)])
+    evs = evs[np.lexsort((evs["i"], evs["step"]))]        # stable: a row's events stay in visit order
+    assert len(evs) == len(ev_ref)
+    for k in ("step", "i", "j", "kind"):
+        assert np.array_equal(evs[k], ev_ref[k]), f"event {k}s differ from the single-GPU run"
+    p1, v1, m1, r1 = nb.split(states[0], n_ref)
+    p2, v2, m2, r2 = nb.split(ref, n_ref)
+    assert np.array_equal(m1.view(np.uint32), m2.view(np.uint32)) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+    assert np.abs(v1 - v2).max() <= 1e-4 * np.abs(v2).max()
+    return ns_ref
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("n0,calls", [(131072, (3,)), (262144, (2, 2))])
+def test_sharded_two_sided_matches_one_gpu(nb, tmp_path, world, n0, calls):
+    """BASELINE-sized discs, several steps per nb_step call."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_calls, args=(world, _free_port(), n0, calls, str(tmp_path), 0, 0, 1.0), nprocs=world, join=True)
+    _check_against_one_gpu(nb, tmp_path, world, n0, calls, 0, 0, 1.0)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_crossing_sort_threshold_inside_one_call(nb, tmp_path, world):
+    """The live body count falls through sort_min_n in the middle of one nb_step(k) call: every rank must keep issuing
+    the same collectives (the per-rank graph choice raced with the device)."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    n0, dense, calls = 49152, 0.5, (6, 2)          # oracle: n = 39844 39250 38791 38208 37505 36732 35879 35050
+    sort_min_n = 38000                            # ... so the count crosses after the 5th step of the first call
+    mp.spawn(_worker_calls, args=(world, _free_port(), n0, calls, str(tmp_path), sort_min_n, 0, dense), nprocs=world, join=True)
+    ns = _check_against_one_gpu(nb, tmp_path, world, n0, calls, sort_min_n, 0, dense)
+    assert ns[0] < sort_min_n < n0, f"the scenario must cross the threshold inside the first call (n after it: {ns[0]})"

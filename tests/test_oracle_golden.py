@@ -120,3 +120,14 @@ def test_rows_match_step(oracle):
     pos, vel, m, r = oracle.split(full, n1)
     assert np.array_equal(pos, allrows[alive][:, 2:4]) and np.array_equal(vel, allrows[alive][:, 0:2])
     assert np.array_equal(m, allrows[alive][:, 4]) and np.array_equal(r, allrows[alive][:, 5])
+
+
+@pytest.mark.parametrize("n", [1, 1000, 16385])
+def test_scenario_generators_match_the_product(oracle, nb, n):
+    """The oracle-side generators of the synthetic BASELINE scenarios (what bench.py's reference arm feeds the
+    reference kernels) produce the very bits of the product's nb_generate."""
+    assert np.array_equal(oracle.init_disc(n, 8e5).view(np.uint32),
+                          nb.generate(nb.SCENARIO_DISC, n, extent=8e5, field_w=800000, field_h=800000).view(np.uint32))
+    assert np.array_equal(oracle.init_two_galaxy(n, 8e5).view(np.uint32),
+                          nb.generate(nb.SCENARIO_TWO_GALAXY, n, extent=8e5, field_w=3000000, field_h=3000000).view(np.uint32))
+    assert np.array_equal(oracle.init_square(n).view(np.uint32), nb.generate(nb.SCENARIO_SQUARE, n).view(np.uint32))
