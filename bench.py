@@ -15,8 +15,10 @@
 
 All: v = 0 (galaxy: bulk + spin), m ~ U[1e4, 1e17], r ~ U[50, 200], dt = 0.2, growth 0.1, collisions on.
 A bench "step" is one pass of the hot path over one batch: `sim_steps_per_step` full time steps (force + collision
-detect/merge + integrate + compaction; 1 for the large configs, 50 for the two 16k ones, whose single step is
-~100 us) issued as ONE nb_step call.  L2 is flushed between bench steps.
+detect/merge + integrate + compaction; 1 for the large configs, 20 for the two 16k ones, whose single step is
+~100 us) issued as ONE nb_step call.  L2 is flushed between bench steps.  The two 16k configs restart every bench step
+from the initial bodies (uploaded outside the timed region): their bodies merge so fast that consecutive batches would
+time ever smaller n; the large configs continue the run from step to step.
 
 One JSON line on stdout (rank 0).  `value` = ordered pairs evaluated by all ranks / device time of the K timed
 steps (CUDA events on the library's stream, max over ranks, bodies resident in HBM).  `e2e` = the same metric
@@ -55,12 +57,15 @@ METRIC = "pairwise_interactions_per_sec"
 UNIT = "interactions/s"
 
 # name: BASELINE index, bodies, scenario, extent, field half-width, coverage, simulation steps per bench step
+# reset: every bench step starts again from the initial bodies (re-uploaded outside the timed region), so that all K steps time
+# the same batch at the configuration's own N -- these scenarios merge fast (the cold 16k disc is down to ~1000 bodies after 400
+# steps); without it consecutive bench steps continue the run.  run_steps: the configuration's whole run, timed once as an extra.
 CONFIGS = {
-    "shipped": dict(idx=0, n=16384, scenario="square", extent=0.0, field=100000, coverage="reference", batch=50),
-    "disc16k": dict(idx=1, n=16384, scenario="disc", extent=1.0e5, field=100000, coverage="full", batch=50),
-    "cluster": dict(idx=2, n=131072, scenario="disc", extent=1.0e5, field=200000, coverage="full", batch=1),
-    "disc1m": dict(idx=3, n=1 << 20, scenario="disc", extent=8.0e5, field=800000, coverage="full", batch=1),
-    "galaxy": dict(idx=4, n=1 << 22, scenario="two_galaxy", extent=8.0e5, field=3000000, coverage="full", batch=1),
+    "shipped": dict(idx=0, n=16384, scenario="square", extent=0.0, field=100000, coverage="reference", batch=20, reset=True, run_steps=2000),
+    "disc16k": dict(idx=1, n=16384, scenario="disc", extent=1.0e5, field=100000, coverage="full", batch=20, reset=True, run_steps=1000),
+    "cluster": dict(idx=2, n=131072, scenario="disc", extent=1.0e5, field=200000, coverage="full", batch=1, reset=False, run_steps=200),
+    "disc1m": dict(idx=3, n=1 << 20, scenario="disc", extent=8.0e5, field=800000, coverage="full", batch=1, reset=False, run_steps=0),
+    "galaxy": dict(idx=4, n=1 << 22, scenario="two_galaxy", extent=8.0e5, field=3000000, coverage="full", batch=1, reset=False, run_steps=0),
 }
 
 
@@ -198,7 +203,10 @@ def run_reference(args, cfg, out_stream) -> int:
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": {"workload": workload_name(args.config, cfg), "bodies": n, "coverage": "reference (the only one it has)",
-                       "sim_steps_per_step": batch, "parallelism": "1 GPU (the reference has no multi-GPU path)"}}
+                       "sim_steps_per_step": batch,
+                       "restart": "every bench step restarts from the initial bodies (outside the timed region)" if cfg["reset"]
+                                  else "consecutive bench steps continue the run",
+                       "parallelism": "1 GPU (the reference has no multi-GPU path)"}}
     have_gpu = False
     if O.gpuref_available():
         try:
@@ -211,20 +219,38 @@ def run_reference(args, cfg, out_stream) -> int:
         cur = n
         pairs = 0
         kernel_ms = 0.0
-        t0 = time.perf_counter()
-        for s in range((args.warmup + args.steps) * batch):
-            if s == args.warmup * batch:
-                t0 = time.perf_counter()
-            cov = O.coverage(cur, O.COVERAGE_REFERENCE)
-            window = 128 * (cov["blocks"] - 1) + cov["limit_last"]
-            cur, ms = ref.step(par)
-            if s >= args.warmup * batch:
-                pairs += cov["n_active"] * max(window - 1, 0)
-                kernel_ms += ms
-        wall = time.perf_counter() - t0
+        wall = 0.0
+        for it in range(args.warmup + args.steps):
+            if cfg["reset"] and it > 0:             # the same batch again: restart from the initial bodies (untimed)
+                ref.close()
+                ref = O.GpuRef(block0, n)
+                cur = n
+            t0 = time.perf_counter()
+            it_pairs, it_ms = 0, 0.0
+            for _ in range(batch):
+                cov = O.coverage(cur, O.COVERAGE_REFERENCE)
+                window = 128 * (cov["blocks"] - 1) + cov["limit_last"]
+                cur, ms = ref.step(par)
+                it_pairs += cov["n_active"] * max(window - 1, 0)
+                it_ms += ms
+            if it >= args.warmup:
+                wall += time.perf_counter() - t0
+                pairs += it_pairs
+                kernel_ms += it_ms
         ref.close()
+        whole = None
+        if cfg["run_steps"] > 0 and not args.no_whole_run:
+            ref = O.GpuRef(block0, n)
+            t0 = time.perf_counter()
+            for _ in range(cfg["run_steps"]):
+                cur_w, _ms = ref.step(par)
+            t_run = time.perf_counter() - t0
+            ref.close()
+            whole = {"sim_steps": cfg["run_steps"], "ms": t_run * 1e3, "sim_steps_per_sec": cfg["run_steps"] / t_run, "bodies_end": cur_w,
+                     "what": "the reference's main-loop body for the configuration's whole run (no image output), wall clock"}
         value = pairs / wall
         base.update({
+            "whole_run": whole,
             "value": value, "ms_per_step": wall / args.steps * 1e3, "steps_per_sec": args.steps / wall,
             "sim_steps_per_sec": args.steps * batch / wall, "bodies_after": cur,
             "kernel_only_value": pairs / (kernel_ms * 1e-3),
@@ -366,6 +392,7 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-whole-run", action="store_true")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.n > 0:
@@ -412,10 +439,15 @@ def main() -> int:
     sim.upload(block0, n)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
+    reset = cfg["reset"]
     for _ in range(args.warmup):
+        if reset:
+            sim.upload(block0, n)
         sim.step(batch)
     sim.sync()
     s0 = sim.stats()
+    pairs_local = 0
+    launches = 0
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -424,6 +456,9 @@ def main() -> int:
     ms_force = 0.0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
+        if reset:                           # the same batch again (nb_upload also resets the statistics)
+            sim.upload(block0, n)
+            s0 = sim.stats()
         flush.zero_()                       # L2 flush between timed iterations (outside the timed events)
         torch.cuda.synchronize()
         if batch == 1:                      # every kernel launched on its own, the force kernel bracketed by events
@@ -432,19 +467,25 @@ def main() -> int:
             t, f = sim.step_timed(batch, force=False)
         ms_total += t
         ms_force += f
+        if reset:
+            s1 = sim.stats()
+            pairs_local += s1["pairs"] - s0["pairs"]
+            launches += s1["kernel_launches"] - s0["kernel_launches"]
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     s1 = sim.stats()
-    pairs_local = s1["pairs"] - s0["pairs"]
-    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    if not reset:
+        pairs_local = s1["pairs"] - s0["pairs"]
+        launches = s1["kernel_launches"] - s0["kernel_launches"]
     sim_steps_timed = args.steps * batch
 
     # ---- correctness of what was just timed ---------------------------------------------------------------
     parity = None
     if want_parity:
         if world > 1:
-            parity = parity_sharded(nb, sim, cfg, block0, dist, rank, world, local, (args.warmup + args.steps) * batch)
+            parity = parity_sharded(nb, sim, cfg, block0, dist, rank, world, local,
+                                    batch if reset else (args.warmup + args.steps) * batch)
         else:
             parity = parity_one_gpu(nb, sim, cfg)
 
@@ -452,6 +493,8 @@ def main() -> int:
     pairs_force = pairs_local
     force_launches = sim_steps_timed
     if batch > 1:
+        if reset:
+            sim.upload(block0, n)
         sf0 = sim.stats()
         force_launches = 8
         _, ms_force = sim.step_timed(force_launches, force=True)
@@ -503,6 +546,17 @@ def main() -> int:
                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
                "what": f"nb_upload(pinned host block) + nb_step({batch}) + nb_download(pinned host block) per step, wall clock"}
 
+    # ---- the configuration's whole run (BASELINE: "1000 steps", "2000 iterations", ...), timed once as an extra --------
+    whole = None
+    if cfg["run_steps"] > 0 and not args.no_whole_run:
+        sim.upload(block0, n)
+        barrier()
+        t_run, _ = sim.step_timed(cfg["run_steps"], force=False)
+        sw = sim.stats()
+        whole = {"sim_steps": cfg["run_steps"], "ms": t_run, "sim_steps_per_sec": cfg["run_steps"] / (t_run * 1e-3),
+                 "bodies_end": sw["n"], "value": float(sw["pairs"]) * world / (t_run * 1e-3) if world == 1 else None,
+                 "what": "nb_upload, then the configuration's whole run as ONE nb_step call (CUDA events around it)"}
+
     if rank == 0:
         peaks = measured_peaks()
         sm_max = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_FALLBACK))
@@ -524,6 +578,8 @@ def main() -> int:
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, cfg), "bodies": n, "coverage": cfg["coverage"],
                        "sim_steps_per_step": batch,
+                       "restart": "every bench step restarts from the initial bodies (uploaded outside the timed region)" if reset
+                                  else "consecutive bench steps continue the run",
                        "parallelism": (f"pair-triangle blocks dealt round-robin to {world} GPUs + NCCL exchange of partial forces, "
                                        f"candidate pairs and post-step rows") if world > 1 else "1 GPU",
                        "l2": "flushed between timed iterations (256 MiB memset); each bench step timed by its own CUDA-event pair",
@@ -563,6 +619,7 @@ def main() -> int:
                       "two_sided": two_sided, "two_sided_regs": s1["sym_regs"]},
             "collision_events": s1["candidates"] - s0["candidates"],
             "parity": parity,
+            "whole_run": whole,
         }
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         # algorithmic bytes per body: finish reads pm 16 + vel 8 + the partial sums (8 each) and writes 24;
