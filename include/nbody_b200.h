@@ -200,10 +200,10 @@ typedef struct nb_plan {
     int32_t row_lo, row_hi, row_act_hi, rows_per_rank, n_iblocks, n_jtiles;
     int64_t units;
     int32_t sorted;           /* 1: the step runs on the cell-sorted order                                   */
-    int32_t two_sided;        /* 1: ... with the two-sided force kernel: the triangle of tile pairs in blocks */
-    int32_t sym_S, sym_Q;     /*    of sym_S x sym_S tile pairs, sym_Q super-tiles per side                   */
-    int32_t sym_blocks;       /*    sym_Q (sym_Q + 1) / 2 blocks; rank r of W takes blocks r, r + W, ...      */
-    int32_t reserved;
+    int32_t two_sided;        /* 1: the step runs the two-sided force kernel: the triangle of tile pairs in    */
+    int32_t sym_S, sym_Q;     /*    blocks of sym_S x sym_S tile pairs, sym_Q super-tiles per side             */
+    int32_t sym_blocks;       /*    sym_Q (sym_Q + 1) / 2 blocks; rank r of W takes work items r, r + W, ...   */
+    int32_t sym_lgu;          /*    a block is 1 << sym_lgu work items (> 0 only when sym_S == 1: few tile pairs) */
 } nb_plan;
 int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out);
 /* Block b (queue order) of the two-sided kernel's pair triangle with Q super-tiles per side -> (R, C), R <= C;

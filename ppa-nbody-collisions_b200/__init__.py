@@ -65,7 +65,7 @@ class Plan(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "blocks", "limit_last", "limit_first", "n_active", "window_len",
                                           "row_lo", "row_hi", "row_act_hi", "rows_per_rank", "n_iblocks", "n_jtiles")]
     _fields_ = _fields_ + [("units", C.c_int64)] + [(k, C.c_int32) for k in ("sorted", "two_sided", "sym_S", "sym_Q",
-                                                                              "sym_blocks", "reserved")]
+                                                                              "sym_blocks", "sym_lgu")]
 
 
 class Config(C.Structure):

@@ -70,6 +70,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *);
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char *(*GetErrorString)(ncclResult_t);
 };
@@ -85,9 +86,10 @@ static NcclApi *nccl_api()
             api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
             api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString) api.lib = h;
+            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy && api.GetErrorString) api.lib = h;
         }
     }
     return api.lib ? &api : nullptr;
@@ -142,7 +144,7 @@ static void free_all(nb_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
     void *ptrs[] = {c->st.absorber, c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
-                    c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.part, c->st.xbuf, c->st.head, c->st.cand,
+                    c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.facc, c->st.xbuf, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -243,17 +245,21 @@ int nb_create(nb_ctx **out, const nb_params *params)
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (st.cap >= min_n) sp.sort_min_n = min_n;
     }
-    // two-sided force kernel on the sorted order
+    // two-sided force kernel: all-pairs coverage; on the cell-sorted order, and on one GPU also on the bodies' own order
     sp.sym = 0;
     sp.sym_grid = 0;
-    sp.sym_qmax = world >= 2 ? kSymQMaxSharded : kSymQMax;
-    if (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
-        ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) {
-        sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
+    sp.sym_min_n = 0;
+    sp.sym_rows = 4;
+    if (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
+        ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || world == 1)) {
         const int socc = force_sym_occupancy(sp.sym_rows, &c->sym_regs);
         if (socc > 0) {
             sp.sym = 1;
             sp.sym_grid = c->sm_count * socc;
+            if (world == 1) {
+                sp.sym_min_n = kSymMinNDefault;
+                if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);       // tuning only
+            }
         }
     }
     sp.lg_parts_override = -1;
@@ -284,18 +290,12 @@ int nb_create(nb_ctx **out, const nb_params *params)
         NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
     }
     if (sp.sym) {
-        // the two-sided kernel keeps one partial sum per body and super-tile: a fixed budget (a rule every rank of
-        // a sharded run evaluates alike) decides whether the capacity is worth it; beyond it the one-sided kernel runs
-        const size_t part_bytes = sizeof(float2) * tiles * kTJ * std::min<size_t>(sp.sym_qmax, tiles);
-        if (part_bytes > ((size_t)48 << 30)) sp.sym = 0;
-    }
-    if (sp.sym) {
-        st.part_stride = tiles * kTJ;
-        NB_ALLOC(st.part, sizeof(float2) * st.part_stride * (size_t)std::min<size_t>(sp.sym_qmax, tiles));
+        st.slots = tiles * kTJ;
+        NB_ALLOC(st.facc, sizeof(long long) * 2 * st.slots);
         if (world > 1) {
             // candidate pairs one rank may contribute per step: its share of the pairs, with room for crowded starts
             st.x_cap = params->candidate_capacity > 0 ? params->candidate_capacity : std::max(131072, st.cap / 4);
-            st.x_stride = (st.part_stride * sizeof(float2) + sizeof(XHeader) + (size_t)st.x_cap * sizeof(int2) + 255) / 256 * 256;
+            st.x_stride = (sizeof(XHeader) + (size_t)st.x_cap * sizeof(int2) + 255) / 256 * 256;
             NB_ALLOC(st.xbuf, st.x_stride * (size_t)world);
             st.cand_cap = (int)std::min<long long>(std::max<long long>(st.cand_cap, (long long)world * st.x_cap), 1LL << 30);
         }
@@ -317,7 +317,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
 #undef NB_ALLOC
     c->sp_plain = sp;
     c->sp_plain.sort_min_n = 0;
-    c->sp_plain.sym = 0;
+    if (world > 1) c->sp_plain.sym = 0;            // sharded: the two-sided kernel runs on the sorted order only
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->host_n, sizeof(int), cudaHostAllocMapped);
     if (e == cudaSuccess) {
@@ -331,6 +331,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     if (e == cudaSuccess) e = cudaMemsetAsync(st.head, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(st.tile_count, 0, sizeof(int) * ctiles, c->stream);
     if (e == cudaSuccess && sp.merge) e = cudaMemsetAsync(st.mhead, 0xff, sizeof(int) * (size_t)st.cap, c->stream);
+    if (e == cudaSuccess && st.facc) e = cudaMemsetAsync(st.facc, 0, sizeof(long long) * 2 * st.slots, c->stream);
     if (e == cudaSuccess) e = launch_plan(st, sp, 0, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
@@ -358,6 +359,7 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
     if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.tile_count, 0, sizeof(int) * ((size_t)(c->st.cap + kCompactTile - 1) / kCompactTile), c->stream));
+    if (c->st.facc) NB_CUDA(c, cudaMemsetAsync(c->st.facc, 0, sizeof(long long) * 2 * c->st.slots, c->stream));
     NB_CUDA(c, launch_ingest(c->st, (const float *)c->dev_block, n, c->stream));
     NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
     if (c->sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, c->sp, c->stream));
@@ -434,9 +436,10 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     NB_CUDA(c, launch_force(c->st, sp, c->variant, c->stream));
     if (f1) NB_CUDA(c, cudaEventRecord(f1, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[1], c->stream));
-    if (sp.sym && sp.sort_min_n > 0 && c->sp.world > 1) {
-        // two-sided kernel on several GPUs: every rank holds a part of every body's force and candidates
-        NB_CUDA(c, launch_sym_reduce(c->st, sp, c->stream));
+    if (sp.sym && c->sp.world > 1) {
+        // two-sided kernel on several GPUs: every rank holds a part of every body's force (fixed-point sums: one exact
+        // integer all-reduce brings them together, the same bits on every rank and as on one GPU) and of the candidates
+        NB_NCCL(c, nccl_api()->AllReduce(c->st.facc, c->st.facc, 2 * c->st.slots, ncclInt64, ncclSum, c->comm, c->stream));
         NB_NCCL(c, nccl_api()->AllGather(c->st.xbuf + (size_t)c->sp.rank * c->st.x_stride, c->st.xbuf, c->st.x_stride, ncclChar, c->comm, c->stream));
         NB_CUDA(c, launch_sym_chain(c->st, sp, c->stream));
     }
@@ -488,14 +491,17 @@ static int run_steps(nb_ctx *c, int n_steps)
     int rc;
     LaunchScope scope(c);
     const bool sortable = c->sp.sort_min_n > 0;
+    const int entry_which = (sortable && *c->host_n >= c->sp.sort_min_n) ? 1 : 0;
     for (int s = 0; s < n_steps; ++s) {
         int which = 0;
         if (sortable && c->sp.world > 1) {
-            // sharded: the two graphs hold different collectives (graph[1] also gathers xbuf), so the choice must be
-            // the same on every rank and cannot depend on how far each host has read ahead of its device.  Always
-            // replay the rich graph: its sort / two-sided kernels exit at once when the step descriptor (identical
-            // on every rank) does not name them.
-            which = 1;
+            // sharded: the two graphs hold different collectives (graph[1] also exchanges the two-sided kernel's sums and
+            // candidates), so the choice must be the same on every rank and cannot depend on how far each host has read
+            // ahead of its device.  It is made once per call from the body count at its start -- every sharded nb_step
+            // and nb_upload ends with a stream synchronisation, and the replicas hold the same bodies, so every rank
+            // reads the same number.  Should the count cross the threshold inside the call, the rich graph's sort and
+            // two-sided kernels exit at once (the step descriptor, identical on every rank, does not name them).
+            which = entry_which;
         } else if (sortable) {
             cudaEvent_t &slot = c->ring[c->ring_pos % 16];
             if (c->ring_pos >= 16) NB_CUDA(c, cudaEventSynchronize(slot));
@@ -623,7 +629,7 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->row_lo = d.row_lo;
     out->row_hi = d.row_hi;
     out->kernel_launches = c->launches;
-    out->force_partials = d.sym ? (c->sp.world > 1 ? c->sp.world : d.sym_Q) : 1;
+    out->force_partials = d.sym ? 2 : 1;       // one 16-byte fixed-point pair, or one float2 slab (two at a CTA boundary)
     return NB_OK;
 }
 
@@ -740,9 +746,11 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (params->n_max >= min_n) sp.sort_min_n = min_n;
     }
-    sp.sym_qmax = sp.world >= 2 ? kSymQMaxSharded : kSymQMax;
-    sp.sym = (sp.sort_min_n > 0 && !(params->flags & NB_FLAG_ONE_SIDED) &&
-              ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault)) ? 1 : 0;
+    sp.sym = (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
+              ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || sp.world == 1)) ? 1 : 0;
+    sp.sym_grid = 3 * 148;                         // the queue granularity rule (sym_lgu) is quoted for a B200
+    sp.sym_min_n = sp.world == 1 ? kSymMinNDefault : 0;
+    sp.field_w = sp.field_h = 1;
     {
         int variant = (params->flags >> NB_FLAG_VARIANT_SHIFT) & 0xf;
         if (params->flags & NB_FLAG_SCALAR_FORCE) variant = 4;
@@ -769,6 +777,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     out->sym_S = d.sym_S;
     out->sym_Q = d.sym_Q;
     out->sym_blocks = d.sym_blocks;
+    out->sym_lgu = d.sym_lgu;
     return NB_OK;
 }
 

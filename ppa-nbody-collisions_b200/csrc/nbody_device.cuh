@@ -12,9 +12,11 @@
 //                                              summed in CTA order by the finish kernel (deterministic)
 //   head [cap] int, cand[cand_cap] int2{j,next} collision candidates: one global list filled through
 //                                              warp-aggregated atomics, threaded into per-row chains
-//   part [<=256][tiles*512] float2            two-sided force kernel: part[Y][slot] = force on the body in `slot` of the
-//                                              cell-sorted order from the bodies of super-tile Y (each written by
-//                                              exactly one block of the pair triangle; summed over Y by finish)
+//   facc [tiles*512][2] int64                  two-sided force kernel: the force on the body in `slot` as 64-bit FIXED-POINT
+//                                              sums (x, y), scale 2^k chosen per step from a bound on |F| (plan).  Every
+//                                              CTA adds its partial sums with RED.ADD.64: integer addition is associative,
+//                                              so the total does not depend on which CTA (or which GPU) took which block
+//                                              -- deterministic without one partial per (body, block) in HBM
 //   tile_count[cap/1024] int                   removed bodies per compaction tile of 1024 bodies
 #pragma once
 #include <cuda_runtime.h>
@@ -36,8 +38,8 @@ constexpr int kSC = 32;                      // j bodies per sub-chunk (granular
 constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
 constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
-constexpr int kSymQMax = 256;                // two-sided force kernel: super-tiles per side of the pair triangle (at most);
-constexpr int kSymQMaxSharded = 512;         //   finer blocks when the triangle is dealt out to several GPUs
+constexpr int kSymSMax = 8;                  // two-sided force kernel: a block of the pair triangle is S x S tile pairs, S <= 8
+constexpr int kSymMinNDefault = 6144;        // smallest n the two-sided kernel takes on the bodies' own order (one GPU)
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
 constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
 
@@ -57,9 +59,14 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
     int lg_parts;                 // a work unit is kTJ >> lg_parts bodies of one j-tile (0 .. kMaxLgParts)
     int sorted;                   // 1: the force kernel streams the cell-sorted j-tiles (jts) this step
-    int sym;                      // 1: this step runs the two-sided (pair-halving) force kernel on the sorted order
-    int sym_S, sym_Q;             //    tiles per super-tile, super-tiles (Q = ceil(T / S) <= kSymQMax)
+    int sym;                      // 1: this step runs the two-sided (pair-halving) force kernel (on the sorted order when
+                                  //    `sorted`, else on the bodies' own order)
+    int sym_S, sym_Q;             //    tiles per super-tile, super-tiles (Q = ceil(T / S))
     int sym_blocks;               //    Q (Q + 1) / 2 blocks of the pair triangle
+    int sym_lgu;                  //    a tile pair is split into 1 << sym_lgu work items of 4 >> sym_lgu rounds (S == 1 only)
+    int sym_items;                //    sym_blocks << sym_lgu items in the work queue
+    float fscale;                 //    fixed-point scale of facc (a power of two)
+    double finv;                  //    1 / fscale
     long long units;              // U = n_iblocks * T << lg_parts  (work units of this rank)
     float rmax;                   // max radius over live bodies
     unsigned step;                // steps since upload
@@ -68,7 +75,10 @@ struct StepDesc {                 // rewritten on the device at the end of every
 struct StepResult {               // accumulated by the scatter kernel, consumed by plan
     unsigned rmax_bits;
     unsigned ticket;
-    unsigned sym_next;            // work queue of the two-sided force kernel: next block of the pair triangle
+    unsigned sym_next;            // work queue of the two-sided force kernel: next item
+    unsigned mmax_bits;           // max mass / min radius over the surviving bodies (float bits; positive floats order like
+    unsigned rmin_inv;            // unsigned ints; the minimum is kept as a maximum of 0x7f800000 - bits so that zero is
+                                  // its neutral start): the bound on |F| behind the fixed-point scale
 };
 
 struct Counters {
@@ -103,7 +113,7 @@ struct StepParams {
     int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
     int sym;                      // 1: steps on the cell-sorted order evaluate each unordered pair once (two-sided kernel)
     int sym_grid;                 //    its grid (resident CTAs x SMs)
-    int sym_qmax;                 //    upper bound of sym_Q (sizes `part`)
+    int sym_min_n;                //    smallest n that runs it on the bodies' own order (one GPU); sorted steps always do
     int sym_rows;                 //    rows per lane: 4 (default), 8 (NB_FLAG_SYM_ROWS8)
 };
 
@@ -119,11 +129,11 @@ struct DevState {
     unsigned *shist;              // 256 x radix blocks
     unsigned char *post;          // world chunks of shard_cap * 24 B
     float2 *fpart;
-    float2 *part;                 // two-sided kernel: [sym_Q][part_stride]
-    size_t part_stride;           //                   slots per super-tile row (tiles * 512)
-    // two-sided kernel on several GPUs: every rank evaluates its share of the triangle's blocks, so forces and
-    // collision candidates of a body are spread over the ranks.  One allgather of `xbuf` per step brings them
-    // together: per rank {float2 F[part_stride]; XHeader; int2 {row, partner}[x_cap]}
+    long long *facc;              // two-sided kernel: [slots][2] fixed-point force sums
+    size_t slots;                 //                   tiles * 512
+    // two-sided kernel on several GPUs: every rank evaluates its share of the triangle's blocks.  The forces meet in
+    // one all-reduce (integer sum) of `facc`; the collision candidates a rank found travel in one allgather of
+    // `xbuf`: per rank {XHeader; int2 {row, partner}[x_cap]}
     unsigned char *xbuf;
     size_t x_stride;              // bytes per rank region
     int x_cap;                    // candidate pairs a rank can contribute per step
@@ -146,17 +156,13 @@ struct XHeader {
     unsigned count;               // candidate pairs this rank found this step
     unsigned pad[3];
 };
-__host__ __device__ inline float2 *x_force(const DevState &st, int rank)
-{
-    return reinterpret_cast<float2 *>(st.xbuf + (size_t)rank * st.x_stride);
-}
 __host__ __device__ inline XHeader *x_header(const DevState &st, int rank)
 {
-    return reinterpret_cast<XHeader *>(st.xbuf + (size_t)rank * st.x_stride + st.part_stride * sizeof(float2));
+    return reinterpret_cast<XHeader *>(st.xbuf + (size_t)rank * st.x_stride);
 }
 __host__ __device__ inline int2 *x_pairs(const DevState &st, int rank)
 {
-    return reinterpret_cast<int2 *>(st.xbuf + (size_t)rank * st.x_stride + st.part_stride * sizeof(float2) + sizeof(XHeader));
+    return reinterpret_cast<int2 *>(st.xbuf + (size_t)rank * st.x_stride + sizeof(XHeader));
 }
 
 __host__ __device__ inline float4 *post_pm(const DevState &st, int rank)
@@ -178,8 +184,7 @@ cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStre
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream_t s);    // nbody_sym.cu
-cudaError_t launch_sym_reduce(const DevState &st, const StepParams &p, cudaStream_t s);   // sharded two-sided kernel: before ...
-cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s);    // ... and after the allgather of xbuf
+cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s);    // sharded two-sided kernel: after the allgather of xbuf
 cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s);
 cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
@@ -193,6 +198,24 @@ int force_sym_occupancy(int rows, int *regs);                             // sam
 constexpr int kForceVariants = 6;
 size_t fpart_slabs(int force_grid, int shard_cap, int iblock);   // slabs of `iblock` float2 needed
 void plan_host(StepDesc *d, const StepParams *p, int n);   // the device plan, run on the host (tests, sharding)
+// Fixed-point scale of the two-sided kernel's force sums for n bodies with masses <= mmax and radii >= rmin in a field
+// of half-width `field`: 2^k with n * mmax / (2 rmin)^2 * 2^k < 2^62.  False when that leaves too little resolution.
+__host__ __device__ inline bool sym_scale(int n, float mmax, float rmin, int field, float *fscale, double *finv)
+{
+    if (n <= 0 || !(mmax > 0.f) || !(rmin > 0.f)) return false;
+    // a pair that is not a hit is at least r_i + r_j >= 2 rmin apart, so no body ever sees more than this
+    const double bound = (double)n * (double)mmax / (4.0 * (double)rmin * (double)rmin);
+    if (!(bound > 0.0) || !(bound < 1.0e300)) return false;
+    const int k = 61 - ilogb(bound);              // bound < 2^(ilogb + 1)  =>  bound * 2^k < 2^62
+    if (k < -120 || k > 120) return false;
+    // one unit is 2^-k; against a typical force n mbar / field^2 that is about 2^-62 (field / (2 rmin))^2 relative:
+    // demand 30 bits below it (float32 carries 24)
+    const double ratio = (double)field / (2.0 * (double)rmin);
+    if (ratio * ratio > 2147483648.0) return false;
+    *fscale = ldexpf(1.0f, k);
+    *finv = ldexp(1.0, -k);
+    return true;
+}
 void sym_block_host(int b, int Q, int *R, int *C);         // two-sided kernel: block b of the queue order -> super-tiles (R, C)
 int sym_block_index_host(int X, int Y, int Q);             //                   and back
 

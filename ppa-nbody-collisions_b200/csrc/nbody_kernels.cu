@@ -19,7 +19,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // plan: the coverage descriptor of the next step (src/nbody.cu:473, :194, :142-143) + sharding
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int n, float rmax, unsigned step)
+__host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int n, float rmax, unsigned step, float mmax,
+                                          float rmin)
 {
     const int T = kGroup;
     d.n = n;
@@ -66,12 +67,27 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.sym_S = 1;
     d.sym_Q = 0;
     d.sym_blocks = 0;
-    if (d.sorted && p.sym) {                      // two-sided kernel: triangle of tile pairs in blocks of S x S
-        const int qmax = p.sym_qmax > 0 ? p.sym_qmax : kSymQMax;
+    d.sym_lgu = 0;
+    d.sym_items = 0;
+    d.fscale = 1.f;
+    d.finv = 1.0;
+    // Two-sided kernel: always on the cell-sorted order; on the bodies' own order (every round pre-tested) from sym_min_n
+    // bodies on, one GPU only.  It needs a fixed-point scale for its force sums; without one the one-sided kernel runs.
+    const bool sym_size = d.sorted || (p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n && n >= 2 * kTJ);
+    if (p.sym && p.coverage == NB_COVERAGE_FULL && sym_size &&
+        sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
+        // the triangle of tile pairs in blocks of S x S; S depends on the tile count alone, so that one GPU and several
+        // cut the work -- and round the partial sums -- alike: their results agree bit for bit
         d.sym = 1;
-        d.sym_S = (d.n_jtiles + qmax - 1) / qmax;
+        int S = d.n_jtiles / 1024;
+        d.sym_S = S < 1 ? 1 : (S > kSymSMax ? kSymSMax : S);
         d.sym_Q = (d.n_jtiles + d.sym_S - 1) / d.sym_S;
         d.sym_blocks = d.sym_Q * (d.sym_Q + 1) / 2;
+        // few tile pairs: split each into 2 or 4 items of 2 or 1 rounds, so that the queue still balances the grid
+        const int grid = p.sym_grid > 0 ? p.sym_grid : 1;
+        if (d.sym_S == 1)
+            while (d.sym_lgu < 2 && ((long long)d.sym_blocks << d.sym_lgu) < 16LL * grid) ++d.sym_lgu;
+        d.sym_items = d.sym_blocks << d.sym_lgu;
     }
     d.rmax = rmax;
     d.step = step;
@@ -81,9 +97,12 @@ __global__ void plan_kernel(DevState st, StepParams p, int n)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     StepDesc d;
-    plan_fill(d, p, n, __uint_as_float(st.res->rmax_bits), 0u);
+    plan_fill(d, p, n, __uint_as_float(st.res->rmax_bits), 0u, __uint_as_float(st.res->mmax_bits),
+              __uint_as_float(0x7f800000u - st.res->rmin_inv));
     *st.desc = d;
     st.res->rmax_bits = 0u;
+    st.res->mmax_bits = 0u;
+    st.res->rmin_inv = 0u;
     st.res->ticket = 0u;
     st.res->sym_next = 0u;
     if (st.xbuf) x_header(st, p.rank)->count = 0u;
@@ -602,25 +621,12 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     const int c_first = unit_owner((long long)ib * TP, U, G);
     const int c_last = unit_owner((long long)(ib + 1) * TP - 1, U, G);
     float fx = 0.f, fy = 0.f;
-    if (d.sym && p.world > 1) {                   // two-sided kernel, sharded: one partial per rank, rank order
-        float lx = 0.f, ly = 0.f;
-        for (int r = 0; r < p.world; ++r) {
-            const float2 v = __ldcs(x_force(st, r) + slot);
-            two_sum(fx, lx, v.x);
-            two_sum(fy, ly, v.y);
-        }
-        fx += lx;
-        fy += ly;
-    } else if (d.sym) {                           // two-sided kernel: one partial per super-tile, fixed order
-        float lx = 0.f, ly = 0.f;
-        const float2 *src = st.part + slot;
-        for (int y = 0; y < d.sym_Q; ++y) {
-            const float2 v = __ldcs(src + (size_t)y * st.part_stride);
-            two_sum(fx, lx, v.x);
-            two_sum(fy, ly, v.y);
-        }
-        fx += lx;
-        fy += ly;
+    if (d.sym) {                                  // two-sided kernel: one exact fixed-point sum per body (all ranks' after the
+        longlong2 *acc = reinterpret_cast<longlong2 *>(st.facc) + slot;        // all-reduce when sharded)
+        const longlong2 a = *acc;
+        *acc = make_longlong2(0, 0);              // ready for the next step
+        fx = (float)((double)a.x * d.finv);
+        fy = (float)((double)a.y * d.finv);
     } else {
         for (int c = c_first; c <= c_last; ++c) {
             const float2 part = st.fpart[(size_t)(c + ib) * IB + within];
@@ -836,7 +842,7 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
         int part = 0;
         for (int t = threadIdx.x; t < ct; t += kCompactThreads) part += kCompactTile - st.tile_count[t];   // tiles < ct are full
         int run = block_sum(part, s_buf);
-        float rmx = 0.f;
+        float rmx = 0.f, mmx = 0.f, rmn = __int_as_float(0x7f800000);
 #pragma unroll 1
         for (int r = 0; r < kCompactTile / kCompactThreads; ++r) {
             const int i = base + r * kCompactThreads + threadIdx.x;
@@ -861,12 +867,20 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
             if (keep) {
                 store_body(st, run + before + __popc(m & ((1u << lane) - 1u)), b, v);
                 rmx = fmaxf(rmx, b.w);
+                mmx = fmaxf(mmx, b.z);
+                rmn = fminf(rmn, b.w);
             }
             run += total;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rmx = fmaxf(rmx, __shfl_xor_sync(0xffffffffu, rmx, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            rmx = fmaxf(rmx, __shfl_xor_sync(0xffffffffu, rmx, o));
+            mmx = fmaxf(mmx, __shfl_xor_sync(0xffffffffu, mmx, o));
+            rmn = fminf(rmn, __shfl_xor_sync(0xffffffffu, rmn, o));
+        }
         if (lane == 0 && rmx > 0.f) atomicMax(&st.res->rmax_bits, __float_as_uint(rmx));
+        if (lane == 0 && mmx > 0.f) atomicMax(&st.res->mmax_bits, __float_as_uint(mmx));
+        if (lane == 0 && rmn >= 0.f) atomicMax(&st.res->rmin_inv, 0x7f800000u - __float_as_uint(rmn));   // min: +0 .. +inf order like uints
     }
     // last CTA to finish plans the next step
     __threadfence();
@@ -891,9 +905,12 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
         c->cand_count = 0;
         c->steps += 1;
         StepDesc d;
-        plan_fill(d, p, n_new, __uint_as_float(__ldcg(&st.res->rmax_bits)), old.step + 1);
+        plan_fill(d, p, n_new, __uint_as_float(__ldcg(&st.res->rmax_bits)), old.step + 1,
+                  __uint_as_float(__ldcg(&st.res->mmax_bits)), __uint_as_float(0x7f800000u - __ldcg(&st.res->rmin_inv)));
         *st.desc = d;
         st.res->rmax_bits = 0u;
+        st.res->mmax_bits = 0u;
+        st.res->rmin_inv = 0u;
         st.res->ticket = 0u;
         st.res->sym_next = 0u;
         if (st.xbuf) x_header(st, p.rank)->count = 0u;
@@ -911,20 +928,28 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevState st, const fl
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pad_end = (n + kTJ - 1) / kTJ * kTJ;
-    float r = 0.f;
+    float r = 0.f, mx = 0.f, rn = __int_as_float(0x7f800000);
     if (i < n) {
         const float2 pos = reinterpret_cast<const float2 *>(block)[i];
         const float2 v = reinterpret_cast<const float2 *>(block + 2 * (size_t)n)[i];
         const float m = block[4 * (size_t)n + i];
         r = block[5 * (size_t)n + i];
+        mx = m;
+        rn = r;
         store_body(st, i, make_float4(pos.x, pos.y, m, r), v);
     } else if (i < pad_end) {
         store_pad(st, i);
     }
     if (i < st.cap) st.head[i] = -1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        rn = fminf(rn, __shfl_xor_sync(0xffffffffu, rn, o));
+    }
     if ((threadIdx.x & 31) == 0 && r > 0.f) atomicMax(&st.res->rmax_bits, __float_as_uint(r));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&st.res->mmax_bits, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0 && rn >= 0.f) atomicMax(&st.res->rmin_inv, 0x7f800000u - __float_as_uint(rn));
 }
 
 __global__ void __launch_bounds__(256) export_kernel(const DevState st, float *__restrict__ block, const int n)
@@ -1110,7 +1135,7 @@ size_t fpart_slabs(int force_grid, int shard_cap, int iblock)
 
 void plan_host(StepDesc *d, const StepParams *p, int n)
 {
-    plan_fill(*d, *p, n, 0.f, 0u);
+    plan_fill(*d, *p, n, 0.f, 0u, 1.0f, 1.0f);     // unit mass and radius: the fixed-point scale always exists
 }
 
 }  // namespace nb

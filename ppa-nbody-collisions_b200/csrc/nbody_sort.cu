@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
         b = st.pm[orig];
         st.sinv[orig] = s;
     }
+    // the two-sided kernel's force sums start every step from zero (on several GPUs finish only clears its own rows)
+    if (st.facc) reinterpret_cast<longlong2 *>(st.facc)[s] = make_longlong2(0, 0);
     float *tile = st.jts + (size_t)blockIdx.x * kSortedTileFloats;
     float *t = tile + threadIdx.x;
     t[0] = b.x;

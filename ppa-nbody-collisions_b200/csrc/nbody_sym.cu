@@ -1,6 +1,5 @@
-// nbody_sym.cu -- the two-sided (pair-halving) force kernel of the cell-sorted order and, for several GPUs, the
-// reduction of its partial forces and the threading of the exchanged candidate pairs.  Same compile flags as
-// nbody_kernels.cu (-fmad=false: every fused multiply-add is explicit).
+// nbody_sym.cu -- the two-sided (pair-halving) force kernel and, for several GPUs, the threading of the exchanged
+// candidate pairs.  Same compile flags as nbody_kernels.cu (-fmad=false: every fused multiply-add is explicit).
 #include "nbody_device.cuh"
 #include "nbody_ptx.cuh"
 
@@ -8,20 +7,36 @@ namespace nb {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// two-sided force kernel (cell-sorted order only): every unordered pair is evaluated once and its force goes
-// to both bodies (Newton's third law).  The collision predicate is symmetric bit for bit, so
-// one evaluation also serves both rows' bookkeeping.
+// Two-sided force kernel: every unordered pair is evaluated once and its force goes to both bodies (Newton's
+// third law).  The collision predicate is symmetric bit for bit, so one evaluation also serves
+// both rows' bookkeeping.
 //
-// Work: the triangle of tile pairs (I, J), J >= I, of the T sorted tiles, cut into blocks of S x S tile pairs
-// (S = ceil(T / 256)); CTAs take blocks from a queue.  A CTA holds the 512 bodies of tile I as rows (4 warp
-// pairs x 32 lanes x 4 rows) and streams the J tiles through the TMA ring.  A J tile is 8 chunks of 64 bodies;
-// in round r = 0..3 warp (k, h) works on chunk 4 h + (k + r) % 4, so all 8 warps are on different chunks and
-// the chunk's j-side sums in shared memory have one writer at a time (block barrier between rounds).
-// Within a round the warp is a systolic ring: every lane owns one pair of j bodies plus their j-side
-// accumulators and hands them to its neighbour after each of the 32 sub-steps (10 SHFL), while its 4 rows stay
-// put.  12 packed f32x2 operations + 2 MUFU per (row, j pair) give four ordered interactions.
-// Results go to part[Y][slot] (Y = super-tile of the other side); each entry has exactly one writer block and
-// a fixed summation order, so the forces do not depend on which CTA took which block.
+// Work: the triangle of tile pairs (I, J), J >= I, of the T 512-body tiles, cut into blocks of S x S tile pairs;
+// CTAs take blocks from a queue (rank r of W takes every W-th).  A CTA holds the 512 bodies of tile I as rows
+// (4 row groups x 2 warps x 32 lanes x 4 rows) and streams the J tiles through a TMA ring.  A J tile is 8 chunks
+// of 64 bodies; in round r = 0..3 warp (k, h) works on chunk 4 h + (k + r) % 4.  Within a round the warp is a
+// systolic ring: every lane owns one pair of j bodies plus their j-side accumulators and hands them to its
+// neighbour after each of the 32 sub-steps (10 SHFL), while its 4 rows stay put.  12 packed f32x2 operations +
+// 2 MUFU per (row, j pair) give four ordered interactions.
+//
+// Sums.  Forces meet in st.facc: per body two 64-bit FIXED-POINT sums (scale 2^k from the step plan).  Row sums
+// of a tile pair are converted once and kept in a thread-private shared-memory accumulator until the CTA leaves
+// the row of tile pairs; j-side sums of a tile pair are combined over the four warps that met the chunk (fixed
+// order) and added at once.  Both go to L2 with RED.ADD.64.  Integer addition is associative: the total does not
+// depend on which CTA or which GPU took which block, so results are reproducible bit for bit and there is no
+// per-(body, block) partial array to write and re-read.
+//
+// Collisions.  Rounds whose bounding boxes may touch (all rounds on the bodies' own order) carry the pre-test
+// d2 <= (r_i + r_max)^2: a pair that passes it is left OUT of the packed sums and its sub-step is flagged in a
+// 32-bit mask per lane; after the round only the flagged (lane, sub-step) pairs are re-evaluated with the
+// reference predicate (src/nbody.cu:126-134) -- a hit becomes a candidate of both rows and gives no force
+// (:215-226), anything else gets its force added scalar-wise on both sides.
+//
+// Synchronisation: one mbarrier phase per tile pair (every thread arrives when its rounds are done); the wait
+// sits one round into the NEXT tile pair, so warps may drift by a round without stalling.  What follows the wait
+// is everything that needs all warps: the j-side combine of the previous tile pair (double-buffered) and the
+// refill of its ring stage.  Thread 0 is the producer: it walks the queue, writes a descriptor per tile pair
+// next to the TMA it issues, and the other threads just consume descriptors until the sentinel.
 // ------------------------------------------------------------------------------------------------
 // Blocks of the pair triangle in queue order: the Q (Q - 1) / 2 full-size blocks (R < C), row by row, then the Q
 // half-size diagonal ones (a short tail).  sym_block_index is the inverse of sym_block_decode.
@@ -32,13 +47,15 @@ __host__ __device__ inline void sym_block_decode(int b, int Q, int &R, int &C)
         R = C = b - noff;
         return;
     }
-    int r = 0, rem = b;
-    while (rem >= Q - 1 - r) {
-        rem -= Q - 1 - r;
-        ++r;
-    }
+    // rows 0 .. r - 1 hold r (2 Q - 1 - r) / 2 blocks: solve for r, then fix the rounding
+    const double q2 = 2.0 * Q - 1.0;
+    int r = (int)((q2 - sqrt(q2 * q2 - 8.0 * (double)b)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > Q - 2) r = Q - 2;
+    while (r > 0 && (long long)r * (2 * Q - 1 - r) / 2 > b) --r;
+    while ((long long)(r + 1) * (2 * Q - 2 - r) / 2 <= b) ++r;
     R = r;
-    C = r + 1 + rem;
+    C = r + 1 + (b - (int)((long long)r * (2 * Q - 1 - r) / 2));
 }
 __host__ __device__ inline int sym_block_index(int X, int Y, int Q)
 {
@@ -47,33 +64,61 @@ __host__ __device__ inline int sym_block_index(int X, int Y, int Q)
     return R * (Q - 1) - R * (R - 1) / 2 + (C - R - 1);
 }
 
-#ifndef NB_SYM_UNROLL
-#define NB_SYM_UNROLL 32
-#endif
-constexpr int kSymUnroll = NB_SYM_UNROLL;   // sub-steps per iteration of the ring loop
 constexpr int kSymThreads = 256;
-constexpr int kSymDynSmem = kStages * kSortedTileFloats * 4;
+constexpr int kSymIpt = 4;                               // rows per lane
+constexpr int kSymStageFloats = 3 * kTJ + 64;            // x, y, m planes + 9 float4 boxes (padded to 128 B)
+constexpr int kSymStageBytes = kSymStageFloats * 4;      // 6400
+constexpr int kSymPlaneBytes = 3 * kTJ * 4;              // 6144
+constexpr int kSymBoxBytes = 4 * (kTJ / kSubPart + 1) * 4;   // 144
+// dynamic shared memory: ring | j-side round results [2][8 warps][4 rounds][32 lanes] float4 | row accumulators
+// [4 rows][2][256 threads] int64
+constexpr int kSymGprivBytes = 2 * 8 * 4 * 32 * 16;      // 32768
+constexpr int kSymAccBytes = kSymIpt * 2 * kSymThreads * 8;   // 16384
+constexpr int kSymDynSmem = kStages * kSymStageBytes + kSymGprivBytes + kSymAccBytes;   // 74752
 
-template <bool TEST, int IPT>
+constexpr unsigned kOwn = 1u, kFirst = 2u, kLast = 4u;   // descriptor flags; bits 4..6 r0, bits 8..10 r1
+
+struct SymProducer {              // thread 0's walk over the work queue (shared memory, used by thread 0 only)
+    int have;                     // inside an item
+    int I, J, I1, J0, J1, diag, r0, r1;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void red_add64(long long *addr, long long v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
+// fixed-point image of a float sum: v * 2^k rounded to the nearest integer (the product is exact)
+__device__ __forceinline__ long long to_fixed(float v, float fscale) { return __float2ll_rn(v * fscale); }
+
+template <bool TEST>
 __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
-                                             const float (&nx)[IPT], const float (&ny)[IPT],
-                                             const float (&nm)[IPT], const float (&thr)[IPT], const float2 s2,
-                                             float2 (&tfx)[IPT], float2 (&tfy)[IPT], bool &cand, const int lane)
+                                             const float (&nx)[kSymIpt], const float (&ny)[kSymIpt],
+                                             const float (&nm)[kSymIpt], const float (&thr)[kSymIpt], const float2 s2,
+                                             float2 (&tfx)[kSymIpt], float2 (&tfy)[kSymIpt], unsigned &mask, const int lane)
 {
     const int src = (lane + 1) & 31;
-#pragma unroll kSymUnroll
-    for (int s = 0; s < 32; ++s) {
 #pragma unroll
-        for (int q = 0; q < IPT; ++q) {
+    for (int s = 0; s < 32; ++s) {
+        bool flagged = false;
+#pragma unroll
+        for (int q = 0; q < kSymIpt; ++q) {
             const float2 dx = __fadd2_rn(xs, make_float2(nx[q], nx[q]));
             const float2 dy = __fadd2_rn(ys, make_float2(ny[q], ny[q]));
             const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, s2));
-            if (TEST) {
-                cand |= (d2.x <= thr[q]);
-                cand |= (d2.y <= thr[q]);
-            }
             const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-            const float2 i3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
+            float2 i3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
+            if (TEST) {                           // a pair that passes the pre-test stays out of the sums
+                const bool f0 = d2.x <= thr[q], f1 = d2.y <= thr[q];
+                i3.x = f0 ? 0.f : i3.x;
+                i3.y = f1 ? 0.f : i3.y;
+                flagged |= f0 | f1;
+            }
             const float2 sj = __fmul2_rn(i3, ms);
             const float2 si = __fmul2_rn(i3, make_float2(nm[q], nm[q]));
             tfx[q] = __ffma2_rn(dx, sj, tfx[q]);
@@ -81,6 +126,7 @@ __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms,
             gx = __ffma2_rn(dx, si, gx);
             gy = __ffma2_rn(dy, si, gy);
         }
+        if (TEST) mask |= flagged ? (1u << s) : 0u;
         xs.x = __shfl_sync(0xffffffffu, xs.x, src);
         xs.y = __shfl_sync(0xffffffffu, xs.y, src);
         ys.x = __shfl_sync(0xffffffffu, ys.x, src);
@@ -114,354 +160,301 @@ __device__ __forceinline__ void push_candidate(const DevState &st, const int ran
     }
 }
 
-// One round redone with the reference predicate (src/nbody.cu:126-134): pairs that hit give no force to either
-// body (:215-226) and become candidates of both rows; `own_tile`: rows and chunk come from the same tile, every
-// ordered pair is met there on its own, so only the row side counts and the self pair is skipped.
-template <int IPT>
-__device__ __noinline__ void sym_exact_round(const DevState &st, const float *tl, const float *rows, const int c,
-                                             const int k, const bool own_tile, const float soft2, const int rank,
-                                             float4 (*acc_s)[kSymThreads], float4 *gacc)
+// The flagged (lane, sub-step) pairs of one round, re-evaluated with the reference predicate.  The ring is home again:
+// lane p holds j pair p and its accumulators; in sub-step s lane l met j pair (l + s) % 32.  Ig / Jg: the tiles in
+// global memory (radius and original-index planes are not staged); `own`: rows and chunk come from the same tile --
+// every ordered pair is met there on its own, so only the row side counts and the self pair is skipped.
+__device__ __forceinline__ void sym_redo(const DevState &st, const float *__restrict__ Ig, const float *__restrict__ Jg,
+                                         const int ibase, const int jbase, const int n, const bool sorted, const int c,
+                                         const int k, const bool own, const float soft2, const int rank, const unsigned mask,
+                                         const float2 xs, const float2 ys, const float2 ms, float2 &gx, float2 &gy,
+                                         const float (&nx)[kSymIpt], const float (&ny)[kSymIpt], const float (&nm)[kSymIpt],
+                                         const float (&thr)[kSymIpt], float2 (&tfx)[kSymIpt], float2 (&tfy)[kSymIpt],
+                                         const int lane, unsigned &n_redo)
 {
-    const int lane = threadIdx.x & 31;
-    const int src = (lane + 1) & 31;
-    float xi[IPT], yi[IPT], mi[IPT], ri[IPT];
-    float2 tfx[IPT], tfy[IPT];
-    int oi[IPT];
-#pragma unroll
-    for (int q = 0; q < IPT; ++q) {
-        const int rs = 32 * IPT * k + 32 * q + lane;
-        xi[q] = rows[rs];
-        yi[q] = rows[kTJ + rs];
-        mi[q] = rows[2 * kTJ + rs];
-        ri[q] = rows[3 * kTJ + rs];
-        oi[q] = __float_as_int(rows[4 * kTJ + rs]);
-        tfx[q] = make_float2(0.f, 0.f);
-        tfy[q] = make_float2(0.f, 0.f);
-    }
-    float2 xs = *reinterpret_cast<const float2 *>(tl + 64 * c + 2 * lane);
-    float2 ys = *reinterpret_cast<const float2 *>(tl + kTJ + 64 * c + 2 * lane);
-    float2 ms = *reinterpret_cast<const float2 *>(tl + 2 * kTJ + 64 * c + 2 * lane);
-    float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
+    unsigned any = __reduce_or_sync(0xffffffffu, mask);
 #pragma unroll 1
-    for (int s = 0; s < 32; ++s) {
-        const int jp = (lane + s) & 31;           // the lane this j pair started on
+    while (any) {
+        const int s = __ffs(any) - 1;
+        any &= any - 1u;
+        ++n_redo;
+        const int p = (lane + s) & 31;
+        const float xj[2] = {__shfl_sync(0xffffffffu, xs.x, p), __shfl_sync(0xffffffffu, xs.y, p)};
+        const float yj[2] = {__shfl_sync(0xffffffffu, ys.x, p), __shfl_sync(0xffffffffu, ys.y, p)};
+        const float mj[2] = {__shfl_sync(0xffffffffu, ms.x, p), __shfl_sync(0xffffffffu, ms.y, p)};
+        float gxe[2] = {0.f, 0.f}, gye[2] = {0.f, 0.f};
+        if ((mask >> s) & 1u) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int js = 64 * c + 2 * jp + e;
-            const float xj = e ? xs.y : xs.x, yj = e ? ys.y : ys.x, mj = e ? ms.y : ms.x;
-            const float rj = tl[3 * kTJ + js];
-            const int oj = __float_as_int(tl[4 * kTJ + js]);
-            float gxe = 0.f, gye = 0.f;
+            for (int e = 0; e < 2; ++e) {
+                const int js = 64 * c + 2 * p + e;
+                const float rj = Jg[3 * kTJ + js];
+                const int oj = sorted ? __float_as_int(Jg[4 * kTJ + js]) : (jbase + js < n ? jbase + js : -1);
 #pragma unroll
-            for (int q = 0; q < IPT; ++q) {
-                const bool valid = (oi[q] >= 0) & (oj >= 0) & !(own_tile & (js == 32 * IPT * k + 32 * q + lane));
-                const float dx = xj - xi[q], dy = yj - yi[q];
-                const float d2 = fmaf(dx, dx, dy * dy);
-                const float rs = ri[q] + rj;
-                const bool hit = d2 <= rs * rs;
-                if (valid && hit) {
-                    push_candidate(st, rank, oi[q], oj);
-                    if (!own_tile) push_candidate(st, rank, oj, oi[q]);
-                } else if (valid) {
-                    const float inv = rsqrt_approx(soft2 > 0.f ? fmaf(dx, dx, fmaf(dy, dy, soft2)) : d2);
-                    const float i3 = (inv * inv) * inv;
-                    const float sj = i3 * mj, si = i3 * -mi[q];
-                    if (e) {
-                        tfx[q].y = fmaf(dx, sj, tfx[q].y);
-                        tfy[q].y = fmaf(dy, sj, tfy[q].y);
-                    } else {
-                        tfx[q].x = fmaf(dx, sj, tfx[q].x);
-                        tfy[q].x = fmaf(dy, sj, tfy[q].x);
+                for (int q = 0; q < kSymIpt; ++q) {
+                    const int rs = 32 * kSymIpt * k + 32 * q + lane;
+                    const float dx = xj[e] + nx[q], dy = yj[e] + ny[q];
+                    const float d2 = fmaf(dx, dx, dy * dy);
+                    const float d2s = soft2 > 0.f ? fmaf(dx, dx, fmaf(dy, dy, soft2)) : d2;
+                    if (d2s <= thr[q]) {                          // else: the pair was part of the packed sums
+                        const float ri = Ig[3 * kTJ + rs];
+                        const int oi = sorted ? __float_as_int(Ig[4 * kTJ + rs]) : (ibase + rs < n ? ibase + rs : -1);
+                        const float rsum = ri + rj;
+                        if (oi < 0 || oj < 0 || (own && js == rs)) {
+                            // padding, or the self pair: nothing
+                        } else if (d2 <= rsum * rsum) {           // src/nbody.cu:126-134
+                            push_candidate(st, rank, oi, oj);
+                            if (!own) push_candidate(st, rank, oj, oi);
+                        } else {
+                            const float inv = rsqrt_approx(d2s);
+                            const float i3 = (inv * inv) * inv;
+                            const float sj = i3 * mj[e], si = i3 * nm[q];
+                            tfx[q].x = fmaf(dx, sj, tfx[q].x);
+                            tfy[q].x = fmaf(dy, sj, tfy[q].x);
+                            gxe[e] = fmaf(dx, si, gxe[e]);
+                            gye[e] = fmaf(dy, si, gye[e]);
+                        }
                     }
-                    gxe = fmaf(dx, si, gxe);
-                    gye = fmaf(dy, si, gye);
                 }
             }
-            if (e) {
-                gx.y += gxe;
-                gy.y += gye;
-            } else {
-                gx.x += gxe;
-                gy.x += gye;
-            }
         }
-        xs.x = __shfl_sync(0xffffffffu, xs.x, src);
-        xs.y = __shfl_sync(0xffffffffu, xs.y, src);
-        ys.x = __shfl_sync(0xffffffffu, ys.x, src);
-        ys.y = __shfl_sync(0xffffffffu, ys.y, src);
-        ms.x = __shfl_sync(0xffffffffu, ms.x, src);
-        ms.y = __shfl_sync(0xffffffffu, ms.y, src);
-        gx.x = __shfl_sync(0xffffffffu, gx.x, src);
-        gx.y = __shfl_sync(0xffffffffu, gx.y, src);
-        gy.x = __shfl_sync(0xffffffffu, gy.x, src);
-        gy.y = __shfl_sync(0xffffffffu, gy.y, src);
-    }
-#pragma unroll
-    for (int q = 0; q < IPT; ++q) {
-        float4 a = acc_s[q][threadIdx.x];
-        two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
-        two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
-        acc_s[q][threadIdx.x] = a;
-    }
-    if (!own_tile) {
-        float4 ga = gacc[32 * c + lane];
-        ga.x += gx.x;
-        ga.y += gx.y;
-        ga.z += gy.x;
-        ga.w += gy.y;
-        gacc[32 * c + lane] = ga;
+        // the j-side corrections go home: lane p receives what lane (p - s) % 32 found for j pair p
+        const int from = (lane - s) & 31;
+        gx.x += __shfl_sync(0xffffffffu, gxe[0], from);
+        gx.y += __shfl_sync(0xffffffffu, gxe[1], from);
+        gy.x += __shfl_sync(0xffffffffu, gye[0], from);
+        gy.y += __shfl_sync(0xffffffffu, gye[1], from);
     }
 }
 
-template <int IPT, int MINB>
-__global__ void __launch_bounds__(kSymThreads, MINB) force_sym_kernel(const DevState st, const StepParams p)
+__global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevState st, const StepParams p)
 {
-    extern __shared__ __align__(128) float tiles_dyn[];
+    extern __shared__ __align__(128) unsigned char sym_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ float4 acc_s[IPT][kSymThreads];        // per thread and row {fx_hi, fx_lo, fy_hi, fy_lo}
-    __shared__ float4 gacc[2][kTJ / 2];                   // per j pair {gx0, gx1, gy0, gy1}, double-buffered over tile pairs
-    __shared__ int s_rc[2];
+    __shared__ __align__(8) unsigned long long done_bar;
+    __shared__ int4 s_desc[kStages];              // per ring stage: {I, J, flags, -}; I < 0: end of work
+    __shared__ SymProducer s_prod;
+    __shared__ float4 s_rb[kSymThreads / 32];     // per warp: bounding box of its 128 rows (sorted order)
     if (!st.desc->sym) return;
-    float(*tiles)[kSortedTileFloats] = reinterpret_cast<float(*)[kSortedTileFloats]>(tiles_dyn);
+    float *ring = reinterpret_cast<float *>(sym_dyn);
+    float4 *gpriv = reinterpret_cast<float4 *>(sym_dyn + kStages * kSymStageBytes);
+    long long *acc_s = reinterpret_cast<long long *>(sym_dyn + kStages * kSymStageBytes + kSymGprivBytes);
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // 512 rows = GROUPS row groups of 32 IPT rows; the HSPLIT warps of a group share its rows and split the 8 chunks
-    // of a J tile: ROUNDS chunks each, one per round
-    constexpr int GROUPS = kTJ / (32 * IPT), HSPLIT = 8 / GROUPS, ROUNDS = 8 / HSPLIT;
-    static_assert(GROUPS * HSPLIT == 8 && ROUNDS == GROUPS, "8 warps, all on different chunks in every round");
-    const int k = warp / HSPLIT, h = warp % HSPLIT;
-    const int T = st.desc->n_jtiles, S = st.desc->sym_S, Q = st.desc->sym_Q;
-    const int nblk = st.desc->sym_blocks;
+    const int k = warp >> 1, h = warp & 1;        // row group, half of the chunks
+    const bool sorted = st.desc->sorted != 0;
+    const int n = st.desc->n;
+    const int tile_floats = sorted ? kSortedTileFloats : kTileFloats;
+    const float *__restrict__ jsrc = sorted ? st.jts : st.jt;
     const float rmax = st.desc->rmax;
+    const float fscale = st.desc->fscale;
     const float2 s2 = make_float2(p.soft2, p.soft2);
     const float Rb = sqrtf((4.f * rmax * rmax + p.soft2) * 1.001f);     // no pre-test can pass beyond this separation
-    const size_t stride = st.part_stride;
+
+    // ---- producer (thread 0) ----------------------------------------------------------------------------
+    unsigned next_item = 0;                       // the item after the current one, fetched one item ahead
+    const unsigned n_items = (unsigned)st.desc->sym_items;
+    auto fetch = [&]() -> unsigned {
+        const unsigned long long b = (unsigned long long)atomicAdd(&st.res->sym_next, 1u) * (unsigned)p.world + (unsigned)p.rank;
+        return b < n_items ? (unsigned)b : 0xffffffffu;
+    };
+    auto produce = [&](const int stage) {         // thread 0: descriptor + TMA of the next tile pair into `stage`
+        SymProducer &P = s_prod;
+        if (!P.have) {
+            const unsigned item = next_item;
+            if (item == 0xffffffffu) {            // queue drained: sentinel (completes the stage's phase without data)
+                s_desc[stage] = make_int4(-1, -1, 0, 0);
+                mbar_arrive(&full_bar[stage]);
+                return;
+            }
+            next_item = fetch();
+            const int lgu = st.desc->sym_lgu, S = st.desc->sym_S, T = st.desc->n_jtiles;
+            int R, C;
+            sym_block_decode((int)(item >> lgu), st.desc->sym_Q, R, C);
+            const int u = (int)(item & ((1u << lgu) - 1u)), rounds = 4 >> lgu;
+            P.diag = R == C;
+            P.I = R * S;
+            P.I1 = min(P.I + S, T);
+            P.J0 = C * S;
+            P.J1 = min(P.J0 + S, T);
+            P.J = P.diag ? P.I : P.J0;
+            P.r0 = u * rounds;
+            P.r1 = P.r0 + rounds;
+            P.have = 1;
+        }
+        const int I = P.I, J = P.J;
+        const unsigned flags = (I == J ? kOwn : 0u) | (J == (P.diag ? I : P.J0) ? kFirst : 0u) | (J == P.J1 - 1 ? kLast : 0u) |
+                               ((unsigned)P.r0 << 4) | ((unsigned)P.r1 << 8);
+        s_desc[stage] = make_int4(I, J, (int)flags, 0);
+        float *dst = ring + stage * kSymStageFloats;
+        const float *src = jsrc + (size_t)J * tile_floats;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (sorted) {
+            mbar_expect_tx(&full_bar[stage], kSymPlaneBytes + kSymBoxBytes);
+            bulk_g2s(dst, src, kSymPlaneBytes, &full_bar[stage]);
+            bulk_g2s(dst + 3 * kTJ, src + 5 * kTJ, kSymBoxBytes, &full_bar[stage]);
+        } else {
+            mbar_expect_tx(&full_bar[stage], kSymPlaneBytes);
+            bulk_g2s(dst, src, kSymPlaneBytes, &full_bar[stage]);
+        }
+        if (++P.J == P.J1) {
+            ++P.I;
+            P.J = P.diag ? P.I : P.J0;
+            if (P.I == P.I1) P.have = 0;
+        }
+    };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&done_bar, kSymThreads);
         fence_barrier_init();
+        s_prod.have = 0;
+        next_item = fetch();
+#pragma unroll 1
+        for (int s = 0; s < kStages; ++s) produce(s);
     }
-    gacc[0][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gacc[1][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 2 * kSymIpt; ++q) acc_s[q * kSymThreads + tid] = 0;
+    __syncthreads();
 
-    auto issue = [&](int stage, int tile) {       // one thread
-        mbar_expect_tx(&full_bar[stage], (unsigned)kSortedTileFloats * 4u);
-        bulk_g2s(tiles[stage], st.jts + (size_t)tile * kSortedTileFloats, (unsigned)kSortedTileFloats * 4u, &full_bar[stage]);
+    float nx[kSymIpt], ny[kSymIpt], nm[kSymIpt];
+    float2 tfx[kSymIpt], tfy[kSymIpt];
+#pragma unroll
+    for (int q = 0; q < kSymIpt; ++q) {
+        nx[q] = ny[q] = nm[q] = 0.f;
+        tfx[q] = make_float2(0.f, 0.f);
+        tfy[q] = make_float2(0.f, 0.f);
+    }
+    int prevJ = -1;                               // the previous tile pair: its j side is combined one round into this one
+    unsigned prev_flags = kOwn;
+    unsigned n_rounds = 0, n_redo = 0, n_culled = 0;
+
+    // everything that needs all warps to be done with tile pair t - 1
+    auto late = [&](const unsigned t) {
+        if (t == 0) return;
+        const unsigned tp = t - 1;
+        mbar_wait(&done_bar, tp & 1u);
+        if (tid == 0) produce((int)(tp % kStages));
+        if (!(prev_flags & kOwn)) {
+            // j side of tile pair t - 1: body pair `lane` of chunk `warp` of tile prevJ <- the four warps that met it
+            const int pr0 = (prev_flags >> 4) & 7, pr1 = (prev_flags >> 8) & 7;
+            const float4 *g = gpriv + (size_t)(tp & 1u) * (8 * 4 * 32);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int r = ((warp & 3) - kk + 4) & 3;
+                if (r >= pr0 && r < pr1) {
+                    const float4 v = g[((2 * kk + (warp >> 2)) * 4 + r) * 32 + lane];
+                    a = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
+                }
+            }
+            long long *dst = st.facc + 2 * ((size_t)prevJ * kTJ + 64 * warp + 2 * lane);      // {gx0, gx1, gy0, gy1}
+            red_add64(dst, to_fixed(a.x, fscale));
+            red_add64(dst + 1, to_fixed(a.z, fscale));
+            red_add64(dst + 2, to_fixed(a.y, fscale));
+            red_add64(dst + 3, to_fixed(a.w, fscale));
+        }
     };
 
-    unsigned it = 0;                              // tile pairs this CTA has consumed: ring position and parity
-    unsigned n_exact = 0, n_culled = 0;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            // several GPUs: rank r takes blocks r, r + world, ... of the same order
-            const long long b = (long long)atomicAdd(&st.res->sym_next, 1u) * p.world + p.rank;
-            int R = -1, C = -1;
-            if (b < nblk) sym_block_decode((int)b, Q, R, C);
-            s_rc[0] = R;
-            s_rc[1] = C;
+    unsigned t = 0;
+#pragma unroll 1
+    for (;; ++t) {
+        const int stage = (int)(t % kStages);
+        mbar_wait(&full_bar[stage], (t / kStages) & 1u);
+        const int4 desc = s_desc[stage];
+        const int I = desc.x, J = desc.y;
+        const unsigned flags = (unsigned)desc.z;
+        if (I < 0) break;
+        const float *tl = ring + stage * kSymStageFloats;
+        const float *__restrict__ Ig = jsrc + (size_t)I * tile_floats;
+        const bool own = flags & kOwn;
+        const int r0 = (flags >> 4) & 7, r1 = (flags >> 8) & 7;
+        if (flags & kFirst) {                     // a new row of tile pairs: this warp's rows
+#pragma unroll
+            for (int q = 0; q < kSymIpt; ++q) {
+                const int rs = 32 * kSymIpt * k + 32 * q + lane;
+                nx[q] = -Ig[rs];
+                ny[q] = -Ig[kTJ + rs];
+                nm[q] = -Ig[2 * kTJ + rs];
+            }
+            if (sorted) {
+                const float4 *bx = reinterpret_cast<const float4 *>(Ig + 5 * kTJ);
+                const float4 b0 = bx[2 * k], b1 = bx[2 * k + 1];
+                if (lane == 0) s_rb[warp] = make_float4(fminf(b0.x, b1.x), fminf(b0.y, b1.y), fmaxf(b0.z, b1.z), fmaxf(b0.w, b1.w));
+                __syncwarp();
+            }
         }
-        __syncthreads();
-        const int R = s_rc[0], C = s_rc[1];
-        if (R < 0) break;
-        const bool diag = R == C;
-        const int I0 = R * S, I1 = min(I0 + S, T), J0 = C * S, J1 = min(J0 + S, T);
-
-        int pI = I0, pJ = diag ? I0 : J0;         // producer cursor (every thread keeps a copy)
-        bool pmore = true;
-        auto padvance = [&]() {
-            if (++pJ == J1) {
-                ++pI;
-                pJ = diag ? pI : J0;
-                if (pI == I1) pmore = false;
-            }
-        };
+        float4 *gp = gpriv + ((size_t)(t & 1u) * 8 + warp) * (4 * 32) + lane;
 #pragma unroll 1
-        for (int s = 0; s < kStages && pmore; ++s) {
-            if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue((int)((it + s) % kStages), pJ);
+        for (int r = r0; r < r1; ++r) {
+            const int c = 4 * h + ((k + r) & 3);
+            bool may_hit = true;
+            if (sorted) {
+                const float4 cb = reinterpret_cast<const float4 *>(tl + 3 * kTJ)[c], rb = s_rb[warp];
+                // (the vote only tells the compiler what is true anyway: the box test is the same in every lane)
+                may_hit = __any_sync(0xffffffffu, !((cb.x - rb.z > Rb) | (rb.x - cb.z > Rb) | (cb.y - rb.w > Rb) | (rb.y - cb.w > Rb)));
             }
-            padvance();
+            float2 xs = *reinterpret_cast<const float2 *>(tl + 64 * c + 2 * lane);
+            float2 ys = *reinterpret_cast<const float2 *>(tl + kTJ + 64 * c + 2 * lane);
+            float2 ms = *reinterpret_cast<const float2 *>(tl + 2 * kTJ + 64 * c + 2 * lane);
+            float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
+            ++n_rounds;
+            if (may_hit) {
+                float thr[kSymIpt];
+#pragma unroll
+                for (int q = 0; q < kSymIpt; ++q) {
+                    const int rs = 32 * kSymIpt * k + 32 * q + lane;
+                    const float rr = Ig[3 * kTJ + rs] + rmax;
+                    const float bound = p.soft2 > 0.f ? (rr * rr + p.soft2) * 1.000001f : rr * rr;
+                    const bool real = sorted ? __float_as_int(Ig[4 * kTJ + rs]) >= 0 : I * kTJ + rs < n;
+                    thr[q] = real ? bound : -1.0f;                    // pads never flag
+                }
+                unsigned mask = 0;
+                sym_substeps<true>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+                if (__any_sync(0xffffffffu, mask != 0u))
+                    sym_redo(st, Ig, jsrc + (size_t)J * tile_floats, I * kTJ, J * kTJ, n, sorted, c, k, own, p.soft2, p.rank,
+                             mask, xs, ys, ms, gx, gy, nx, ny, nm, thr, tfx, tfy, lane, n_redo);
+            } else {
+                const float thr[kSymIpt] = {0.f, 0.f, 0.f, 0.f};
+                unsigned mask = 0;
+                sym_substeps<false>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+                ++n_culled;
+            }
+            if (r == r0) late(t);                 // one round of slack for the slowest warp of the previous tile pair
+            gp[r * 32] = make_float4(gx.x, gx.y, gy.x, gy.y);
         }
-
-#pragma unroll 1
-        for (int I = I0; I < I1; ++I) {
-            const float *rows = st.jts + (size_t)I * kSortedTileFloats;
-            float nx[IPT], ny[IPT], nm[IPT], thr[IPT];
+        // bank this tile pair's row sums: exact from here on
 #pragma unroll
-            for (int q = 0; q < IPT; ++q) {
-                const int rs = 32 * IPT * k + 32 * q + lane;
-                nx[q] = -rows[rs];
-                ny[q] = -rows[kTJ + rs];
-                nm[q] = -rows[2 * kTJ + rs];
-                const float rr = rows[3 * kTJ + rs] + rmax;
-                const float bound = p.soft2 > 0.f ? (rr * rr + p.soft2) * 1.000001f : rr * rr;
-                thr[q] = __float_as_int(rows[4 * kTJ + rs]) >= 0 ? bound : -1.0f;      // pads never flag
-                acc_s[q][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            // row-side sums of the rounds since the last fold (registers); banked in the compensated shared
-            // accumulators before every pre-tested round and at the end of every tile pair
-            float2 tfx[IPT], tfy[IPT];
-#pragma unroll
-            for (int q = 0; q < IPT; ++q) {
-                tfx[q] = make_float2(0.f, 0.f);
-                tfy[q] = make_float2(0.f, 0.f);
-            }
-            auto fold_rows = [&]() {
-#pragma unroll
-                for (int q = 0; q < IPT; ++q) {
-                    float4 a = acc_s[q][tid];
-                    two_sum(a.x, a.y, tfx[q].x + tfx[q].y);
-                    two_sum(a.z, a.w, tfy[q].x + tfy[q].y);
-                    acc_s[q][tid] = a;
-                    tfx[q] = make_float2(0.f, 0.f);
-                    tfy[q] = make_float2(0.f, 0.f);
-                }
-            };
-            float4 rb;                            // bounding box of this warp's 128 rows
-            {
-                const float4 *bx = reinterpret_cast<const float4 *>(rows + 5 * kTJ);
-                constexpr int BOXES = 32 * IPT / kSubPart;        // 64-body boxes per row group
-                rb = bx[BOXES * k];
-#pragma unroll
-                for (int e = 1; e < BOXES; ++e) {
-                    const float4 b = bx[BOXES * k + e];
-                    rb = make_float4(fminf(rb.x, b.x), fminf(rb.y, b.y), fmaxf(rb.z, b.z), fmaxf(rb.w, b.w));
-                }
-            }
-#pragma unroll 1
-            for (int J = diag ? I : J0; J < J1; ++J, ++it) {
-                const int stage = (int)(it % kStages);
-                mbar_wait(&full_bar[stage], (it / kStages) & 1u);
-                const float *tl = tiles[stage];
-                const bool own = J == I;
-                const int buf = (int)(it & 1u);
-#pragma unroll 1
-                for (int r = 0; r < ROUNDS; ++r) {
-                    const int c = ROUNDS * h + ((k + r) % ROUNDS);
-                    const float4 cb = reinterpret_cast<const float4 *>(tl + 5 * kTJ)[c];
-                    const bool may_hit = !((cb.x - rb.z > Rb) | (rb.x - cb.z > Rb) | (cb.y - rb.w > Rb) | (rb.y - cb.w > Rb));
-                    float2 xs = *reinterpret_cast<const float2 *>(tl + 64 * c + 2 * lane);
-                    float2 ys = *reinterpret_cast<const float2 *>(tl + kTJ + 64 * c + 2 * lane);
-                    float2 ms = *reinterpret_cast<const float2 *>(tl + 2 * kTJ + 64 * c + 2 * lane);
-                    float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
-                    bool cand = false;
-                    if (may_hit) {
-                        // the round's row sums must be separable (they are dropped if the pre-test fires):
-                        // bank what earlier rounds left in the registers first
-                        fold_rows();
-                        sym_substeps<true, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
-                    } else {
-                        sym_substeps<false, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, cand, lane);
-                        ++n_culled;
-                    }
-                    if (may_hit && __any_sync(0xffffffffu, cand)) {
-                        // rare: a possible hit somewhere in the round; its sums are dropped and the round redone
-                        sym_exact_round<IPT>(st, tl, rows, c, k, own, p.soft2, p.rank, acc_s, gacc[buf]);
-                        n_exact += 2;
-#pragma unroll
-                        for (int q = 0; q < IPT; ++q) {
-                            tfx[q] = make_float2(0.f, 0.f);
-                            tfy[q] = make_float2(0.f, 0.f);
-                        }
-                    } else if (!own) {
-                        float4 ga = gacc[buf][32 * c + lane];
-                        ga.x += gx.x;
-                        ga.y += gx.y;
-                        ga.z += gy.x;
-                        ga.w += gy.y;
-                        gacc[buf][32 * c + lane] = ga;
-                    }
-                    __syncthreads();
-                }
-                fold_rows();
-                // every warp is done with the stage: refill it with the tile pair kStages ahead
-                if (tid == 0 && pmore) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(stage, pJ);
-                }
-                if (pmore) padvance();
-                if (!own) {
-                    // j side of this tile pair: bodies 2 tid, 2 tid + 1 of tile J <- the rows of tile I.  The first
-                    // tile of the block's rows writes, the others add (same CTA, program order).
-                    const float4 ga = gacc[buf][tid];
-                    gacc[buf][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 *dst = reinterpret_cast<float4 *>(st.part + (size_t)R * stride + (size_t)J * kTJ) + tid;
-                    float4 v = make_float4(ga.x, ga.z, ga.y, ga.w);       // {gx0, gy0, gx1, gy1}
-                    if (I != I0) {
-                        const float4 o = *dst;
-                        v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
-                    }
-                    *dst = v;
-                }
-            }
-            // i side of the finished row of tile pairs: the two warps that share these rows, in fixed order
-            __syncthreads();
-            if (h == 0) {
-                float2 *dst = st.part + (size_t)C * stride + (size_t)I * kTJ + 32 * IPT * k + lane;
-#pragma unroll
-                for (int q = 0; q < IPT; ++q) {
-                    float4 a = acc_s[q][tid];
-#pragma unroll
-                    for (int e = 1; e < HSPLIT; ++e) {
-                        const float4 b = acc_s[q][tid + 32 * e];
-                        two_sum(a.x, a.y, b.x);
-                        two_sum(a.z, a.w, b.z);
-                        a.y += b.y;
-                        a.w += b.w;
-                    }
-                    float2 v = make_float2(a.x + a.y, a.z + a.w);
-                    if (diag && I != I0) {        // the diagonal block's rows already hold j-side sums of earlier tiles
-                        const float2 o = dst[32 * q];
-                        v = make_float2(o.x + v.x, o.y + v.y);
-                    }
-                    dst[32 * q] = v;
-                }
-            }
-            __syncthreads();
+        for (int q = 0; q < kSymIpt; ++q) {
+            acc_s[(2 * q) * kSymThreads + tid] += to_fixed(tfx[q].x + tfx[q].y, fscale);
+            acc_s[(2 * q + 1) * kSymThreads + tid] += to_fixed(tfy[q].x + tfy[q].y, fscale);
+            tfx[q] = make_float2(0.f, 0.f);
+            tfy[q] = make_float2(0.f, 0.f);
         }
+        if (flags & kLast) {                      // leaving this row of tile pairs: the rows' sums go to the global accumulators
+            long long *dst = st.facc + 2 * ((size_t)I * kTJ + 32 * kSymIpt * k + lane);
+#pragma unroll
+            for (int q = 0; q < kSymIpt; ++q) {
+                red_add64(dst + 64 * q, acc_s[(2 * q) * kSymThreads + tid]);
+                red_add64(dst + 64 * q + 1, acc_s[(2 * q + 1) * kSymThreads + tid]);
+                acc_s[(2 * q) * kSymThreads + tid] = 0;
+                acc_s[(2 * q + 1) * kSymThreads + tid] = 0;
+            }
+        }
+        prevJ = J;
+        prev_flags = flags;
+        mbar_arrive(&done_bar);                   // (release) this thread's round results of tile pair t are in place
     }
+    late(t);                                      // j side of the last tile pair
     if (p.count_stats && lane == 0) {
-        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)it * (2ull * ROUNDS));   // rounds x 2 sub-chunks of 32 bodies
-        atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_exact);
+        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)n_rounds * 2ull);   // a round = 2 sub-chunks of 32 bodies
+        atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_redo);           // sub-steps re-evaluated exactly
         atomicAdd(&st.ctr->culled_parts, (unsigned long long)n_culled);
     }
 }
 
-// Sharded two-sided kernel, before the allgather: this rank's partial force on every slot = the sum, in
-// super-tile order, of the part[][] entries its own blocks wrote.
-__global__ void __launch_bounds__(256) sym_reduce_kernel(const DevState st, const StepParams p)
-{
-    const StepDesc &d = *st.desc;
-    if (!d.sym) return;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= d.n) return;
-    const int X = slot / kTJ / d.sym_S, Q = d.sym_Q, W = p.world, me = p.rank;
-    float fx = 0.f, fy = 0.f, lx = 0.f, ly = 0.f;
-    const float2 *src = st.part + slot;
-    auto add = [&](int y) {
-        const float2 v = __ldcs(src + (size_t)y * st.part_stride);
-        two_sum(fx, lx, v.x);
-        two_sum(fy, ly, v.y);
-    };
-    // super-tiles before X: block (y, X) has index y (Q - 1) - y (y - 1) / 2 + X - y - 1, stepping by Q - 2 - y
-    int b = X - 1;
-    for (int y = 0; y < X; ++y) {
-        if (b % W == me) add(y);
-        b += Q - 2 - y;
-    }
-    if (sym_block_index(X, X, Q) % W == me) add(X);
-    // super-tiles after X: block (X, y), consecutive indices, so every W-th one is this rank's
-    if (X + 1 < Q) {
-        const int b0 = sym_block_index(X, X + 1, Q);
-        int first = (me - b0 % W + W) % W;
-        for (int y = X + 1 + first; y < Q; y += W) add(y);
-    }
-    x_force(st, p.rank)[slot] = make_float2(fx + lx, fy + ly);
-}
-
-// ... and after it: thread every rank's candidate pairs whose row this rank finishes into the rows' chains
+// Sharded two-sided kernel, after the allgather of xbuf: thread every rank's candidate pairs whose row this rank
+// finishes into the rows' chains
 __global__ void __launch_bounds__(256) sym_chain_kernel(const DevState st, const StepParams p)
 {
     const StepDesc &d = *st.desc;
@@ -474,7 +467,7 @@ __global__ void __launch_bounds__(256) sym_chain_kernel(const DevState st, const
         const int2 *src = x_pairs(st, r);
         for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
             const int2 pr = src[e];
-            const int slot = st.sinv[pr.x];
+            const int slot = d.sorted ? st.sinv[pr.x] : pr.x;
             if (slot < d.row_lo || slot >= d.row_hi) continue;
             const unsigned idx = (unsigned)r * (unsigned)st.x_cap + e;      // cand holds world * x_cap entries
             const int prev = atomicExch(&st.head[pr.x], (int)idx);
@@ -491,17 +484,7 @@ __global__ void __launch_bounds__(256) sym_chain_kernel(const DevState st, const
 
 cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream_t s)
 {
-    if (p.sym_rows == 8)
-        force_sym_kernel<8, 2><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
-    else
-        force_sym_kernel<4, 3><<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_sym_reduce(const DevState &st, const StepParams &p, cudaStream_t s)
-{
-    sym_reduce_kernel<<<(st.cap + 255) / 256, 256, 0, s>>>(st, p);
+    force_sym_kernel<<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -515,17 +498,12 @@ cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream
 
 int force_sym_occupancy(int rows, int *regs)
 {
+    (void)rows;
     int occ = 0;
     cudaFuncAttributes fa = {};
-    if (rows == 8) {
-        cudaFuncSetAttribute(force_sym_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel<8, 2>, kSymThreads, kSymDynSmem);
-        cudaFuncGetAttributes(&fa, force_sym_kernel<8, 2>);
-    } else {
-        cudaFuncSetAttribute(force_sym_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel<4, 3>, kSymThreads, kSymDynSmem);
-        cudaFuncGetAttributes(&fa, force_sym_kernel<4, 3>);
-    }
+    cudaFuncSetAttribute(force_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel, kSymThreads, kSymDynSmem);
+    cudaFuncGetAttributes(&fa, force_sym_kernel);
     if (regs) *regs = fa.numRegs;
     return occ;
 }

@@ -437,6 +437,24 @@ def test_two_sided_force_kernel(nb, oracle, n, field, steps, softening):
     assert st["exact_chunks"] > 0
 
 
+@pytest.mark.parametrize("n,field,steps", [(8000, 20000, 5), (7000, 30000, 4), (16384, 60000, 6), (16384, 100000, 8)])
+def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps):
+    """Below the sort threshold one GPU runs the two-sided kernel on the bodies' own order (every round pre-tested, tile pairs
+    split into quarter work items), down to 6144 bodies; the first two scenarios fall through that bound while running
+    (oracle: 8000 -> 5071 and 7000 -> 5780 after the first step), so two-sided and one-sided steps follow each other."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL)
+    sim.upload(block0, n)
+    assert sim.stats()["pair_halving"] == 1 and sim.stats()["sym_regs"] > 0
+    sim.close()
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field)
+    assert st["culled_parts"] == 0 and st["exact_chunks"] > 0
+    assert st["pair_halving"] == (1 if st["n"] >= 6144 else 0)
+    _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_GRAPH)
+    st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_ONE_SIDED)
+    assert st["pair_halving"] == 0 and st["sym_regs"] == 0
+
+
 def test_two_sided_is_deterministic_and_agrees_with_one_sided(nb):
     """N = 131 072 disc at the shipped surface density, 4 steps: two runs of the two-sided kernel are bit-identical
     (every partial sum has one writer and a fixed order although blocks are taken from a queue), and against the
