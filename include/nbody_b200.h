@@ -221,6 +221,13 @@ int nb_probe_fp32(int device, double *tflops);
 /* ---- render (src/nbody.cu:294-348, 350-371) ------------------------------ */
 /* Rasterise the current bodies into a w*h 8-bit image (background 254, body 0). */
 int nb_render(nb_ctx *ctx, uint8_t *image, int w, int h);
+/*
+ * The same with the reference's launch grid: its loop draws with the grid of the step it has just done,
+ * floor(n_before / 128) blocks of 128 threads (src/nbody.cu:473,535), so only bodies below grid_threads =
+ * 128 * max(1, n_before / 128) are drawn -- up to 127 tail bodies are missing from its pictures.  The drop-in driver
+ * uses this; threads beyond the live bodies (where the reference reads outside its body store) draw nothing here.
+ */
+int nb_render_grid(nb_ctx *ctx, uint8_t *image, int w, int h, int grid_threads);
 /* Write a binary P5 file exactly as saveImageToDisk does (header "P5\n<w> <h>\n255\n"). */
 int nb_write_pgm(const char *path, const uint8_t *image, int w, int h);
 

@@ -131,6 +131,37 @@ int gpuref_step(float dt, float growth, int field_w, int field_h, float *kernel_
     return new_n;
 }
 
+/*
+ * The reference's image of the CURRENT bodies, launched as its main loop does (src/nbody.cu:529-539): background
+ * 254, then generateImage<<<blocks, 128, 128 * (sizeof(Vec2f) + sizeof(float))>>> with `blocks` taken from
+ * `grid_n` -- the loop re-uses the step's grid, floor(n_before_the_step / 128) blocks, so bodies at and beyond
+ * 128 * blocks are not drawn.  Launches whose grid has threads beyond the live bodies read outside the body store in
+ * the reference (positions[i], radii[i] for i >= numBodies): those are refused here (-4) instead of pinned.
+ */
+int gpuref_render(int width, int height, int field_w, int field_h, int grid_n, unsigned char *img_out)
+{
+    if (!g_open) return -1;
+    if (width <= 0 || height <= 0 || !img_out) return -2;
+    const int blocks = ref_blocks(grid_n);
+    if (blocks * THREADS_PER_BLOCK > g_n) return -4;
+    const size_t image_size = (size_t)width * height;
+    char *d_img = nullptr;
+    cudaStream_t image_stream;
+    cudaStreamCreate(&image_stream);                                                             /* :457 */
+    g_bodies.uploadToDevice();                                                                   /* :532 */
+    cudaMalloc((void **)&d_img, image_size);                                                     /* :533 */
+    cudaMemsetAsync(d_img, 254, image_size, image_stream);                                       /* :534 */
+    generateImage<<<blocks, THREADS_PER_BLOCK, THREADS_PER_BLOCK * (sizeof(Vec2f) + sizeof(float)), image_stream>>>(
+        g_bodies.d_contiguousData, g_bodies.numBodies, d_img, width, height, field_w, field_h);  /* :535-536 */
+    cudaMemcpyAsync(img_out, d_img, image_size, cudaMemcpyDeviceToHost, image_stream);           /* :537 */
+    cudaError_t err = cudaStreamSynchronize(image_stream);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    cudaFree(d_img);
+    cudaStreamDestroy(image_stream);
+    /* the step path uploads again only if the device copy is gone (BodiesData::uploadToDevice, :88-96) */
+    return err == cudaSuccess ? 0 : -100 - (int)err;
+}
+
 void gpuref_close()
 {
     if (!g_open) return;

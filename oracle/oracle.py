@@ -228,6 +228,8 @@ def gpuref() -> C.CDLL:
         G.gpuref_time_kernels.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                           C.c_int, C.c_int, fp]
         G.gpuref_main_in.argtypes = [C.c_char_p]
+        if hasattr(G, "gpuref_render"):
+            G.gpuref_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _gref = G
     return _gref
 
@@ -246,6 +248,15 @@ class GpuRef:
         if n < 0:
             raise RuntimeError(f"gpuref_step failed: {n}")
         return n, float(ms.value)
+
+    def render(self, width: int, height: int, field_w: int, field_h: int, grid_n: int) -> np.ndarray:
+        """The reference's generateImage of the current bodies, launched with the grid of a step that started with
+        grid_n bodies (src/nbody.cu:529-539).  Raises when that launch would read outside the body store."""
+        img = np.zeros((height, width), dtype=np.uint8)
+        rc = gpuref().gpuref_render(width, height, field_w, field_h, grid_n, img.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"gpuref_render failed: {rc}")
+        return img
 
     def read(self):
         n = gpuref().gpuref_n()

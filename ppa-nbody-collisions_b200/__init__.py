@@ -34,7 +34,7 @@ UNIQUE_ID_BYTES = 128
 SYMBOLS = [
     "nb_create", "nb_destroy", "nb_last_error", "nb_version", "nb_upload", "nb_download", "nb_num_bodies",
     "nb_step", "nb_step_timed", "nb_step_profile", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
-    "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_render", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
+    "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_render", "nb_render_grid", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
     "nb_rng_fval_range", "nb_generate", "nb_probe_fp32",
 ]
 
@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
     L.nb_plan_block.argtypes = [C.c_int, C.c_int, ip, ip]
     L.nb_plan_block_index.argtypes = [C.c_int, C.c_int, C.c_int]
     L.nb_render.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.nb_render_grid.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.nb_write_pgm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
     L.nb_config_parse.argtypes = [C.c_char_p, C.POINTER(Config), C.c_int]
     L.nb_rng_seed.argtypes = [C.POINTER(Rng), C.c_uint64]
@@ -291,9 +292,14 @@ class Simulation:
         self._check("nb_events", lib().nb_events(self._h, buf.ctypes.data, capacity, C.byref(cnt)))
         return buf[:cnt.value]
 
-    def render(self, w: int, h: int) -> np.ndarray:
+    def render(self, w: int, h: int, grid_n: int | None = None) -> np.ndarray:
+        """All live bodies, or -- with grid_n, the body count before the last step -- what the reference's stale launch
+        grid draws (nb_render_grid)."""
         img = np.zeros((h, w), dtype=np.uint8)
-        self._check("nb_render", lib().nb_render(self._h, img.ctypes.data, w, h))
+        if grid_n is None:
+            self._check("nb_render", lib().nb_render(self._h, img.ctypes.data, w, h))
+        else:
+            self._check("nb_render_grid", lib().nb_render_grid(self._h, img.ctypes.data, w, h, 128 * max(1, grid_n // 128)))
         return img
 
     def comm_init(self, unique_id: bytes):

@@ -249,7 +249,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.sym = 0;
     sp.sym_grid = 0;
     sp.sym_min_n = 0;
-    sp.sym_rows = 4;
+    sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
+    if (const char *e = getenv("NBODY_B200_SYM_ROWS")) sp.sym_rows = atoi(e) == 8 ? 8 : 4;                // tuning only
     if (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
         ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || world == 1)) {
         const int socc = force_sym_occupancy(sp.sym_rows, &c->sym_regs);
@@ -708,9 +709,11 @@ int nb_comm_init(nb_ctx *c, const void *id_bytes)
     return NB_OK;
 }
 
-int nb_render(nb_ctx *c, uint8_t *image, int w, int h)
+int nb_render(nb_ctx *c, uint8_t *image, int w, int h) { return nb_render_grid(c, image, w, h, 0x7fffffff); }
+
+int nb_render_grid(nb_ctx *c, uint8_t *image, int w, int h, int grid_threads)
 {
-    if (!c || !image || w <= 0 || h <= 0) return NB_ERR_INVALID;
+    if (!c || !image || w <= 0 || h <= 0 || grid_threads < 0) return NB_ERR_INVALID;
     StepDesc d;
     int rc = fetch_state(c, &d, nullptr);
     if (rc != NB_OK) return rc;
@@ -724,7 +727,7 @@ int nb_render(nb_ctx *c, uint8_t *image, int w, int h)
     }
     LaunchScope scope(c);
     NB_CUDA(c, cudaMemsetAsync(c->dev_img, 254, bytes, c->stream));      // src/nbody.cu:534
-    NB_CUDA(c, launch_render(c->st, d.n, c->dev_img, w, h, c->sp.field_w, c->sp.field_h, c->stream));
+    NB_CUDA(c, launch_render(c->st, std::min(d.n, grid_threads), c->dev_img, w, h, c->sp.field_w, c->sp.field_h, c->stream));
     NB_CUDA(c, cudaMemcpyAsync(image, c->dev_img, bytes, cudaMemcpyDeviceToHost, c->stream));
     NB_CUDA(c, cudaStreamSynchronize(c->stream));
     return NB_OK;
@@ -748,7 +751,8 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     }
     sp.sym = (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
               ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || sp.world == 1)) ? 1 : 0;
-    sp.sym_grid = 3 * 148;                         // the queue granularity rule (sym_lgu) is quoted for a B200
+    sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
+    sp.sym_grid = (sp.sym_rows == 8 ? 2 : 3) * 148; // the queue granularity rule (sym_lgu) is quoted for a B200
     sp.sym_min_n = sp.world == 1 ? kSymMinNDefault : 0;
     sp.field_w = sp.field_h = 1;
     {

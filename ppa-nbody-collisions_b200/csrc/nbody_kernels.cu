@@ -85,8 +85,9 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
         d.sym_blocks = d.sym_Q * (d.sym_Q + 1) / 2;
         // few tile pairs: split each into 2 or 4 items of 2 or 1 rounds, so that the queue still balances the grid
         const int grid = p.sym_grid > 0 ? p.sym_grid : 1;
+        const int max_lgu = p.sym_rows == 8 ? 1 : 2;      // a tile pair is 2 (8 rows per lane) or 4 rounds
         if (d.sym_S == 1)
-            while (d.sym_lgu < 2 && ((long long)d.sym_blocks << d.sym_lgu) < 16LL * grid) ++d.sym_lgu;
+            while (d.sym_lgu < max_lgu && ((long long)d.sym_blocks << d.sym_lgu) < 16LL * grid) ++d.sym_lgu;
         d.sym_items = d.sym_blocks << d.sym_lgu;
     }
     d.rmax = rmax;
@@ -1041,8 +1042,8 @@ cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, c
         return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !p.sym || p.sort_min_n <= 0) return e;
-    // sort-capable step: whichever kernel the step descriptor does not name returns at once
+    if (e != cudaSuccess || !p.sym) return e;
+    // a context that can run the two-sided kernel: whichever kernel the step descriptor does not name returns at once
     return launch_force_sym(st, p, s);
 }
 

@@ -16,6 +16,8 @@
 //                        conserves mass and momentum; not reference behaviour)
 //   --one-sided          never use the two-sided (pair-halving) force kernel (full coverage, >= 40960 bodies)
 //   --no-images          skip rendering and image files
+//   --render MODE        reference (default: the bodies the reference's stale launch grid draws, src/nbody.cu:473,535:
+//                        those below 128 * floor(n_before_the_step / 128)) | all (every live body)
 //   --dump-state PATH    write the final BodiesData block (int32 n, then 24 n bytes)
 //   --resume PATH        start from a --dump-state file instead of generating initial conditions
 //                        (checkpoint / resume: the reference has none)
@@ -51,7 +53,7 @@ int main(int argc, char **argv)
     int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
     unsigned long long seed = 1024;
     double extent = 0, softening = 0;
-    bool images = true, conserving = false, one_sided = false;
+    bool images = true, conserving = false, one_sided = false, render_all = false;
     for (int a = 1; a < argc; ++a) {
         const std::string opt = argv[a];
         auto need = [&](const char *name) -> const char * {
@@ -76,6 +78,7 @@ int main(int argc, char **argv)
         else if (opt == "--merge") conserving = std::string(need("--merge")) == "conserving";
         else if (opt == "--one-sided") one_sided = true;
         else if (opt == "--no-images") images = false;
+        else if (opt == "--render") render_all = std::string(need("--render")) == "all";
         else if (opt == "--dump-state") dump_state = need("--dump-state");
         else if (opt == "--dump-events") dump_events = need("--dump-events");
         else if (opt == "--resume") resume = need("--resume");
@@ -158,6 +161,8 @@ int main(int argc, char **argv)
     std::vector<uint8_t> img(do_images ? (size_t)cfg.imgWidth * cfg.imgHeight : 0);
     int pending = -1;                               // iteration whose image waits to be saved
     for (int it = 0; it < total; ++it) {
+        int n_before = 0;                           // the reference draws with the grid of the step it has just done
+        if (do_images && it % every == 0 && !render_all && (rc = nb_num_bodies(ctx, &n_before)) != NB_OK) die(ctx, "nb_num_bodies", rc);
         if ((rc = nb_step(ctx, 1)) != NB_OK) die(ctx, "nb_step", rc);
         if (do_images) {
             // the image rendered after iteration k is written during iteration k + 1 (:513-522)
@@ -172,7 +177,8 @@ int main(int argc, char **argv)
                 pending = -1;
             }
             if (it % every == 0) {                  // :529-539
-                if ((rc = nb_render(ctx, img.data(), cfg.imgWidth, cfg.imgHeight)) != NB_OK) die(ctx, "nb_render", rc);
+                const int grid = render_all ? 0x7fffffff : 128 * (n_before < 128 ? 1 : n_before / 128);                  // :473,535
+                if ((rc = nb_render_grid(ctx, img.data(), cfg.imgWidth, cfg.imgHeight, grid)) != NB_OK) die(ctx, "nb_render", rc);
                 pending = it;
             }
         }

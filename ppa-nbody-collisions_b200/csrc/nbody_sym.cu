@@ -65,16 +65,25 @@ __host__ __device__ inline int sym_block_index(int X, int Y, int Q)
 }
 
 constexpr int kSymThreads = 256;
-constexpr int kSymIpt = 4;                               // rows per lane
 constexpr int kSymStageFloats = 3 * kTJ + 64;            // x, y, m planes + 9 float4 boxes (padded to 128 B)
 constexpr int kSymStageBytes = kSymStageFloats * 4;      // 6400
 constexpr int kSymPlaneBytes = 3 * kTJ * 4;              // 6144
 constexpr int kSymBoxBytes = 4 * (kTJ / kSubPart + 1) * 4;   // 144
-// dynamic shared memory: ring | j-side round results [2][8 warps][4 rounds][32 lanes] float4 | row accumulators
-// [4 rows][2][256 threads] int64
-constexpr int kSymGprivBytes = 2 * 8 * 4 * 32 * 16;      // 32768
-constexpr int kSymAccBytes = kSymIpt * 2 * kSymThreads * 8;   // 16384
-constexpr int kSymDynSmem = kStages * kSymStageBytes + kSymGprivBytes + kSymAccBytes;   // 74752
+// Geometry for IPT rows per lane: the 512 rows are GROUPS = 16 / IPT row groups of 32 IPT rows; the HSPLIT = 8 / GROUPS warps
+// of a group share its rows and split the 8 chunks of a J tile: ROUNDS = GROUPS chunks each, one per round; in round r
+// warp (k, h) works on chunk ROUNDS h + (k + r) % ROUNDS, so the 8 warps are always on 8 different chunks.
+//   IPT = 4: 4 groups x 2 warps, 4 rounds, <= 80 registers, 3 CTAs per SM  (10 SHFL per 4 rows and sub-step)
+//   IPT = 8: 2 groups x 4 warps, 2 rounds, <= 128 registers, 2 CTAs per SM (10 SHFL per 8 rows and sub-step)
+// dynamic shared memory: ring | j-side round results [2][8 warps][ROUNDS][32 lanes] float4 | row accumulators
+// [IPT rows][2][256 threads] int64
+template <int IPT>
+struct SymGeom {
+    static constexpr int kGroups = 16 / IPT, kHsplit = 8 / kGroups, kRounds = kGroups;
+    static constexpr int kGprivBytes = 2 * 8 * kRounds * 32 * 16;
+    static constexpr int kAccBytes = IPT * 2 * kSymThreads * 8;
+    static constexpr int kDynSmem = kStages * kSymStageBytes + kGprivBytes + kAccBytes;     // 74752 either way
+    static constexpr int kMinBlocks = IPT == 4 ? 3 : 2;
+};
 
 constexpr unsigned kOwn = 1u, kFirst = 2u, kLast = 4u;   // descriptor flags; bits 4..6 r0, bits 8..10 r1
 
@@ -96,18 +105,18 @@ __device__ __forceinline__ void red_add64(long long *addr, long long v)
 // fixed-point image of a float sum: v * 2^k rounded to the nearest integer (the product is exact)
 __device__ __forceinline__ long long to_fixed(float v, float fscale) { return __float2ll_rn(v * fscale); }
 
-template <bool TEST>
+template <bool TEST, int IPT>
 __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
-                                             const float (&nx)[kSymIpt], const float (&ny)[kSymIpt],
-                                             const float (&nm)[kSymIpt], const float (&thr)[kSymIpt], const float2 s2,
-                                             float2 (&tfx)[kSymIpt], float2 (&tfy)[kSymIpt], unsigned &mask, const int lane)
+                                             const float (&nx)[IPT], const float (&ny)[IPT],
+                                             const float (&nm)[IPT], const float (&thr)[IPT], const float2 s2,
+                                             float2 (&tfx)[IPT], float2 (&tfy)[IPT], unsigned &mask, const int lane)
 {
     const int src = (lane + 1) & 31;
 #pragma unroll
     for (int s = 0; s < 32; ++s) {
         bool flagged = false;
 #pragma unroll
-        for (int q = 0; q < kSymIpt; ++q) {
+        for (int q = 0; q < IPT; ++q) {
             const float2 dx = __fadd2_rn(xs, make_float2(nx[q], nx[q]));
             const float2 dy = __fadd2_rn(ys, make_float2(ny[q], ny[q]));
             const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, s2));
@@ -164,12 +173,13 @@ __device__ __forceinline__ void push_candidate(const DevState &st, const int ran
 // lane p holds j pair p and its accumulators; in sub-step s lane l met j pair (l + s) % 32.  Ig / Jg: the tiles in
 // global memory (radius and original-index planes are not staged); `own`: rows and chunk come from the same tile --
 // every ordered pair is met there on its own, so only the row side counts and the self pair is skipped.
+template <int IPT>
 __device__ __forceinline__ void sym_redo(const DevState &st, const float *__restrict__ Ig, const float *__restrict__ Jg,
                                          const int ibase, const int jbase, const int n, const bool sorted, const int c,
                                          const int k, const bool own, const float soft2, const int rank, const unsigned mask,
                                          const float2 xs, const float2 ys, const float2 ms, float2 &gx, float2 &gy,
-                                         const float (&nx)[kSymIpt], const float (&ny)[kSymIpt], const float (&nm)[kSymIpt],
-                                         const float (&thr)[kSymIpt], float2 (&tfx)[kSymIpt], float2 (&tfy)[kSymIpt],
+                                         const float (&nx)[IPT], const float (&ny)[IPT], const float (&nm)[IPT],
+                                         const float (&thr)[IPT], float2 (&tfx)[IPT], float2 (&tfy)[IPT],
                                          const int lane, unsigned &n_redo)
 {
     unsigned any = __reduce_or_sync(0xffffffffu, mask);
@@ -190,8 +200,8 @@ __device__ __forceinline__ void sym_redo(const DevState &st, const float *__rest
                 const float rj = Jg[3 * kTJ + js];
                 const int oj = sorted ? __float_as_int(Jg[4 * kTJ + js]) : (jbase + js < n ? jbase + js : -1);
 #pragma unroll
-                for (int q = 0; q < kSymIpt; ++q) {
-                    const int rs = 32 * kSymIpt * k + 32 * q + lane;
+                for (int q = 0; q < IPT; ++q) {
+                    const int rs = 32 * IPT * k + 32 * q + lane;
                     const float dx = xj[e] + nx[q], dy = yj[e] + ny[q];
                     const float d2 = fmaf(dx, dx, dy * dy);
                     const float d2s = soft2 > 0.f ? fmaf(dx, dx, fmaf(dy, dy, soft2)) : d2;
@@ -226,8 +236,11 @@ __device__ __forceinline__ void sym_redo(const DevState &st, const float *__rest
     }
 }
 
-__global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevState st, const StepParams p)
+template <int IPT>
+__global__ void __launch_bounds__(kSymThreads, SymGeom<IPT>::kMinBlocks) force_sym_kernel(const DevState st, const StepParams p)
 {
+    using G = SymGeom<IPT>;
+    constexpr int HSPLIT = G::kHsplit, ROUNDS = G::kRounds;
     extern __shared__ __align__(128) unsigned char sym_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
     __shared__ __align__(8) unsigned long long done_bar;
@@ -237,10 +250,10 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
     if (!st.desc->sym) return;
     float *ring = reinterpret_cast<float *>(sym_dyn);
     float4 *gpriv = reinterpret_cast<float4 *>(sym_dyn + kStages * kSymStageBytes);
-    long long *acc_s = reinterpret_cast<long long *>(sym_dyn + kStages * kSymStageBytes + kSymGprivBytes);
+    long long *acc_s = reinterpret_cast<long long *>(sym_dyn + kStages * kSymStageBytes + G::kGprivBytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = warp >> 1, h = warp & 1;        // row group, half of the chunks
+    const int k = warp / HSPLIT, h = warp % HSPLIT;   // row group, share of the chunks
     const bool sorted = st.desc->sorted != 0;
     const int n = st.desc->n;
     const int tile_floats = sorted ? kSortedTileFloats : kTileFloats;
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             const int lgu = st.desc->sym_lgu, S = st.desc->sym_S, T = st.desc->n_jtiles;
             int R, C;
             sym_block_decode((int)(item >> lgu), st.desc->sym_Q, R, C);
-            const int u = (int)(item & ((1u << lgu) - 1u)), rounds = 4 >> lgu;
+            const int u = (int)(item & ((1u << lgu) - 1u)), rounds = ROUNDS >> lgu;
             P.diag = R == C;
             P.I = R * S;
             P.I1 = min(P.I + S, T);
@@ -314,13 +327,13 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         for (int s = 0; s < kStages; ++s) produce(s);
     }
 #pragma unroll
-    for (int q = 0; q < 2 * kSymIpt; ++q) acc_s[q * kSymThreads + tid] = 0;
+    for (int q = 0; q < 2 * IPT; ++q) acc_s[q * kSymThreads + tid] = 0;
     __syncthreads();
 
-    float nx[kSymIpt], ny[kSymIpt], nm[kSymIpt];
-    float2 tfx[kSymIpt], tfy[kSymIpt];
+    float nx[IPT], ny[IPT], nm[IPT];
+    float2 tfx[IPT], tfy[IPT];
 #pragma unroll
-    for (int q = 0; q < kSymIpt; ++q) {
+    for (int q = 0; q < IPT; ++q) {
         nx[q] = ny[q] = nm[q] = 0.f;
         tfx[q] = make_float2(0.f, 0.f);
         tfy[q] = make_float2(0.f, 0.f);
@@ -336,15 +349,15 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         mbar_wait(&done_bar, tp & 1u);
         if (tid == 0) produce((int)(tp % kStages));
         if (!(prev_flags & kOwn)) {
-            // j side of tile pair t - 1: body pair `lane` of chunk `warp` of tile prevJ <- the four warps that met it
+            // j side of tile pair t - 1: body pair `lane` of chunk `warp` of tile prevJ <- the GROUPS warps that met it
             const int pr0 = (prev_flags >> 4) & 7, pr1 = (prev_flags >> 8) & 7;
-            const float4 *g = gpriv + (size_t)(tp & 1u) * (8 * 4 * 32);
+            const float4 *g = gpriv + (size_t)(tp & 1u) * (8 * ROUNDS * 32);
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int r = ((warp & 3) - kk + 4) & 3;
+            for (int kk = 0; kk < G::kGroups; ++kk) {
+                const int r = ((warp % ROUNDS) - kk + ROUNDS) % ROUNDS;
                 if (r >= pr0 && r < pr1) {
-                    const float4 v = g[((2 * kk + (warp >> 2)) * 4 + r) * 32 + lane];
+                    const float4 v = g[((HSPLIT * kk + warp / ROUNDS) * ROUNDS + r) * 32 + lane];
                     a = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
                 }
             }
@@ -371,23 +384,30 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         const int r0 = (flags >> 4) & 7, r1 = (flags >> 8) & 7;
         if (flags & kFirst) {                     // a new row of tile pairs: this warp's rows
 #pragma unroll
-            for (int q = 0; q < kSymIpt; ++q) {
-                const int rs = 32 * kSymIpt * k + 32 * q + lane;
+            for (int q = 0; q < IPT; ++q) {
+                const int rs = 32 * IPT * k + 32 * q + lane;
                 nx[q] = -Ig[rs];
                 ny[q] = -Ig[kTJ + rs];
                 nm[q] = -Ig[2 * kTJ + rs];
             }
             if (sorted) {
                 const float4 *bx = reinterpret_cast<const float4 *>(Ig + 5 * kTJ);
-                const float4 b0 = bx[2 * k], b1 = bx[2 * k + 1];
-                if (lane == 0) s_rb[warp] = make_float4(fminf(b0.x, b1.x), fminf(b0.y, b1.y), fmaxf(b0.z, b1.z), fmaxf(b0.w, b1.w));
+                constexpr int BOXES = 32 * IPT / kSubPart;            // 64-body boxes per row group
+                float4 b = bx[BOXES * k];
+#pragma unroll
+                for (int e = 1; e < BOXES; ++e) {
+                    const float4 o = bx[BOXES * k + e];
+                    b = make_float4(fminf(b.x, o.x), fminf(b.y, o.y), fmaxf(b.z, o.z), fmaxf(b.w, o.w));
+                }
+                __syncwarp();
+                if (lane == 0) s_rb[warp] = b;
                 __syncwarp();
             }
         }
-        float4 *gp = gpriv + ((size_t)(t & 1u) * 8 + warp) * (4 * 32) + lane;
+        float4 *gp = gpriv + ((size_t)(t & 1u) * 8 + warp) * (ROUNDS * 32) + lane;
 #pragma unroll 1
         for (int r = r0; r < r1; ++r) {
-            const int c = 4 * h + ((k + r) & 3);
+            const int c = ROUNDS * h + ((k + r) % ROUNDS);
             bool may_hit = true;
             if (sorted) {
                 const float4 cb = reinterpret_cast<const float4 *>(tl + 3 * kTJ)[c], rb = s_rb[warp];
@@ -400,24 +420,24 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
             float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
             ++n_rounds;
             if (may_hit) {
-                float thr[kSymIpt];
+                float thr[IPT];
 #pragma unroll
-                for (int q = 0; q < kSymIpt; ++q) {
-                    const int rs = 32 * kSymIpt * k + 32 * q + lane;
+                for (int q = 0; q < IPT; ++q) {
+                    const int rs = 32 * IPT * k + 32 * q + lane;
                     const float rr = Ig[3 * kTJ + rs] + rmax;
                     const float bound = p.soft2 > 0.f ? (rr * rr + p.soft2) * 1.000001f : rr * rr;
                     const bool real = sorted ? __float_as_int(Ig[4 * kTJ + rs]) >= 0 : I * kTJ + rs < n;
                     thr[q] = real ? bound : -1.0f;                    // pads never flag
                 }
                 unsigned mask = 0;
-                sym_substeps<true>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+                sym_substeps<true, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
                 if (__any_sync(0xffffffffu, mask != 0u))
-                    sym_redo(st, Ig, jsrc + (size_t)J * tile_floats, I * kTJ, J * kTJ, n, sorted, c, k, own, p.soft2, p.rank,
+                    sym_redo<IPT>(st, Ig, jsrc + (size_t)J * tile_floats, I * kTJ, J * kTJ, n, sorted, c, k, own, p.soft2, p.rank,
                              mask, xs, ys, ms, gx, gy, nx, ny, nm, thr, tfx, tfy, lane, n_redo);
             } else {
-                const float thr[kSymIpt] = {0.f, 0.f, 0.f, 0.f};
+                const float thr[IPT] = {};
                 unsigned mask = 0;
-                sym_substeps<false>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+                sym_substeps<false, IPT>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
                 ++n_culled;
             }
             if (r == r0) late(t);                 // one round of slack for the slowest warp of the previous tile pair
@@ -425,16 +445,16 @@ __global__ void __launch_bounds__(kSymThreads, 3) force_sym_kernel(const DevStat
         }
         // bank this tile pair's row sums: exact from here on
 #pragma unroll
-        for (int q = 0; q < kSymIpt; ++q) {
+        for (int q = 0; q < IPT; ++q) {
             acc_s[(2 * q) * kSymThreads + tid] += to_fixed(tfx[q].x + tfx[q].y, fscale);
             acc_s[(2 * q + 1) * kSymThreads + tid] += to_fixed(tfy[q].x + tfy[q].y, fscale);
             tfx[q] = make_float2(0.f, 0.f);
             tfy[q] = make_float2(0.f, 0.f);
         }
         if (flags & kLast) {                      // leaving this row of tile pairs: the rows' sums go to the global accumulators
-            long long *dst = st.facc + 2 * ((size_t)I * kTJ + 32 * kSymIpt * k + lane);
+            long long *dst = st.facc + 2 * ((size_t)I * kTJ + 32 * IPT * k + lane);
 #pragma unroll
-            for (int q = 0; q < kSymIpt; ++q) {
+            for (int q = 0; q < IPT; ++q) {
                 red_add64(dst + 64 * q, acc_s[(2 * q) * kSymThreads + tid]);
                 red_add64(dst + 64 * q + 1, acc_s[(2 * q + 1) * kSymThreads + tid]);
                 acc_s[(2 * q) * kSymThreads + tid] = 0;
@@ -484,7 +504,10 @@ __global__ void __launch_bounds__(256) sym_chain_kernel(const DevState st, const
 
 cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream_t s)
 {
-    force_sym_kernel<<<p.sym_grid, kSymThreads, kSymDynSmem, s>>>(st, p);
+    if (p.sym_rows == 8)
+        force_sym_kernel<8><<<p.sym_grid, kSymThreads, SymGeom<8>::kDynSmem, s>>>(st, p);
+    else
+        force_sym_kernel<4><<<p.sym_grid, kSymThreads, SymGeom<4>::kDynSmem, s>>>(st, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -496,17 +519,24 @@ cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream
     return cudaGetLastError();
 }
 
-int force_sym_occupancy(int rows, int *regs)
+template <int IPT>
+static int sym_occupancy(int *regs)
 {
-    (void)rows;
     int occ = 0;
     cudaFuncAttributes fa = {};
-    cudaFuncSetAttribute(force_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSymDynSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel, kSymThreads, kSymDynSmem);
-    cudaFuncGetAttributes(&fa, force_sym_kernel);
+    cudaFuncSetAttribute(force_sym_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SymGeom<IPT>::kDynSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_sym_kernel<IPT>, kSymThreads, SymGeom<IPT>::kDynSmem);
+    cudaFuncGetAttributes(&fa, force_sym_kernel<IPT>);
     if (regs) *regs = fa.numRegs;
     return occ;
 }
+
+int force_sym_occupancy(int rows, int *regs)
+{
+    return rows == 8 ? sym_occupancy<8>(regs) : sym_occupancy<4>(regs);
+}
+
+int force_sym_rounds(int rows) { return rows == 8 ? SymGeom<8>::kRounds : SymGeom<4>::kRounds; }
 
 void sym_block_host(int b, int Q, int *R, int *C)
 {

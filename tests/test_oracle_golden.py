@@ -131,3 +131,26 @@ def test_scenario_generators_match_the_product(oracle, nb, n):
     assert np.array_equal(oracle.init_two_galaxy(n, 8e5).view(np.uint32),
                           nb.generate(nb.SCENARIO_TWO_GALAXY, n, extent=8e5, field_w=3000000, field_h=3000000).view(np.uint32))
     assert np.array_equal(oracle.init_square(n).view(np.uint32), nb.generate(nb.SCENARIO_SQUARE, n).view(np.uint32))
+
+
+def _render_golden(golden_dir):
+    p = golden_dir / "render_golden.json"
+    if not p.exists():
+        pytest.skip("tests/golden/render_golden.json not generated yet (tools/make_golden_render.py on a GPU box)")
+    return json.loads(p.read_text())
+
+
+def test_render_restatement_matches_the_reference_images(oracle, golden_dir):
+    """orc_render against images of the UNMODIFIED generateImage kernel (src/nbody.cu:294-348), launched with the
+    reference loop's own grid: byte-exact (FNV of the image bytes), including the bodies its stale grid leaves out."""
+    g = _render_golden(golden_dir)
+    for name, sc in g["scenarios"].items():
+        assert sc["oracle_byte_exact"], name
+        block = oracle.init_square(sc["n"], field_w=sc["field"], field_h=sc["field"], min_radius=sc["min_radius"],
+                                   max_radius=sc["max_radius"])
+        par = oracle.params(field_w=sc["field"], field_h=sc["field"], coverage=oracle.COVERAGE_REFERENCE)
+        n = sc["n"]
+        for _ in range(sc["steps"]):
+            n, _, _ = oracle.step(block, n, par)
+        img = oracle.render(block, min(n, sc["drawn"]), sc["width"], sc["height"], sc["field"], sc["field"])
+        assert f"{oracle.fnv(img):016x}" == sc["fnv"] and int((img == 0).sum()) == sc["body_pixels"], name

@@ -263,6 +263,60 @@ def test_render_matches_reference_rasteriser(nb, oracle):
     sim.close()
 
 
+def test_render_matches_the_reference_images(nb, oracle, golden_dir):
+    """nb_render_grid against images of the UNMODIFIED generateImage kernel (tests/golden/render_golden.json, made by
+    tools/make_golden_render.py on a B200) and, when oracle/_ref is on the box, against that kernel run live."""
+    p = golden_dir / "render_golden.json"
+    if not p.exists():
+        pytest.skip("tests/golden/render_golden.json not generated yet")
+    g = json.loads(p.read_text())
+    live = oracle.gpuref_available()
+    for name, sc in g["scenarios"].items():
+        n, field = sc["n"], sc["field"]
+        block = oracle.init_square(n, field_w=field, field_h=field, min_radius=sc["min_radius"], max_radius=sc["max_radius"])
+        sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_REFERENCE)
+        sim.upload(block, n)
+        ref = oracle.GpuRef(block, n) if live else None
+        par = oracle.params(field_w=field, field_h=field, coverage=oracle.COVERAGE_REFERENCE)
+        grid_n = n
+        for _ in range(sc["steps"]):
+            grid_n = sim.num_bodies()
+            sim.step(1)
+            if ref is not None:
+                ref.step(par)
+        img = sim.render(sc["width"], sc["height"], grid_n=grid_n)
+        assert f"{oracle.fnv(img):016x}" == sc["fnv"] and int((img == 0).sum()) == sc["body_pixels"], name
+        if ref is not None:
+            assert np.array_equal(img, ref.render(sc["width"], sc["height"], field, field, grid_n)), f"{name}: live reference image"
+            ref.close()
+        if sc["drawn"] < n:                       # nb_render itself draws every live body
+            assert int((sim.render(sc["width"], sc["height"]) == 0).sum()) >= sc["body_pixels"]
+        sim.close()
+
+
+def test_oracle_matches_the_reference_kernels_live(oracle):
+    """The pin of the oracle to the reference, re-run instead of replayed: the UNMODIFIED ComputeForces / MoveBodies
+    (oracle/_ref, on the box whenever the build container made it) against oracle/nbody_oracle.c, bit for bit, on
+    tiling-edge sizes and on the shipped scenario."""
+    if not oracle.gpuref_available():
+        pytest.skip("oracle/_ref/libnbody_gpuref.so is not on this box")
+    for n0, field, steps in ((129, 2000, 4), (300, 2000, 5), (1000, 2000, 5), (4096, 20000, 6), (16384, 100000, 12)):
+        block = oracle.init_square(n0, field_w=field, field_h=field)
+        par = oracle.params(field_w=field, field_h=field, coverage=oracle.COVERAGE_REFERENCE)
+        ref = oracle.GpuRef(block, n0)
+        cpu, n_cpu = block.copy(), n0
+        for s in range(steps):
+            n_ref, _ = ref.step(par)
+            n_cpu, _, _ = oracle.step(cpu, n_cpu, par)
+            assert n_ref == n_cpu, f"n0 = {n0}, step {s}: survivors"
+            if n_ref == 0:
+                break
+            got, _ = ref.read()
+            assert np.array_equal(got[:6 * n_ref].view(np.uint32), cpu[:6 * n_cpu].view(np.uint32)), f"n0 = {n0}, step {s}: state bits"
+        if n_cpu > 0:
+            ref.close()
+
+
 def test_drop_in_driver(nb, oracle, tmp_path):
     """The `nbody` executable on a config file: banner, echo, image files on the reference's schedule
     (src/nbody.cu:513-539), final state equal to the oracle's after the same number of steps."""
@@ -289,7 +343,8 @@ def test_drop_in_driver(nb, oracle, tmp_path):
     for s in range(8):
         if s == 1:
             first = (tmp_path / "imgs" / "iteration_0.ppm").read_bytes()
-            assert first == b"P5\n64 48\n255\n" + oracle.render(block, n, 64, 48, 2000, 2000).tobytes()
+            # like the reference, the driver draws with the grid of the step it has just done: 128 * floor(300 / 128) bodies
+            assert first == b"P5\n64 48\n255\n" + oracle.render(block, min(n, 256), 64, 48, 2000, 2000).tobytes()
         n, _, ev = oracle.step(block, n, par, want_events=True)
         ev_rows += [f"{s},{e['i']},{e['j']},{e['kind']}" for e in ev]
     raw = (tmp_path / "state.bin").read_bytes()
