@@ -527,11 +527,19 @@ def main() -> int:
         barrier()
         d2h = 0
         pairs_e2e = 0.0
+        phase = [0.0, 0.0, 0.0]                 # host-side split of the e2e time: upload | step (returns early on one GPU) | download
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            ta = time.perf_counter()
             sim.upload_ptr(host_in.data_ptr(), n)
+            tb = time.perf_counter()
             sim.step(batch)
+            tc = time.perf_counter()
             n_out = sim.download_ptr(host_out.data_ptr(), n)
+            td = time.perf_counter()
+            phase[0] += tb - ta
+            phase[1] += tc - tb
+            phase[2] += td - tc
             d2h += 24 * n_out
         barrier()
         t_e2e = time.perf_counter() - t0
@@ -544,6 +552,8 @@ def main() -> int:
             t_e2e, pairs_e2e = float(tm[0]), float(t_t[1])
         e2e = {"value": pairs_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 24 * n,
                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
+               "host_ms_per_step": {"nb_upload": phase[0] / e2e_steps * 1e3, "nb_step": phase[1] / e2e_steps * 1e3,
+                                    "nb_download": phase[2] / e2e_steps * 1e3, "rank": 0},
                "what": f"nb_upload(pinned host block) + nb_step({batch}) + nb_download(pinned host block) per step, wall clock"}
 
     # ---- the configuration's whole run (BASELINE: "1000 steps", "2000 iterations", ...), timed once as an extra --------

@@ -81,7 +81,7 @@ typedef struct nb_params {
                                  n >= sort_min_n, every step runs on a Morton-cell-sorted copy of the bodies so that
                                  the collision pre-test is skipped for (rows, j part) pairs whose bounding boxes are
                                  apart; results keep the bodies' own order, events and survivors are unchanged     */
-#define NB_FLAG_MERGE_CONSERVING 16 /* opt-in physics beyond parity (single GPU): instead of the reference's "heavier
+#define NB_FLAG_MERGE_CONSERVING 16 /* opt-in physics beyond parity (every force path, any number of GPUs): instead of the reference's "heavier
                                  absorbs, nothing is conserved" rule (src/nbody.cu:215-226), every body points at the
                                  lowest index among itself and its hit partners; following the pointers ends at a root,
                                  which takes mass, momentum (at the post-force velocities) and growth * radius of

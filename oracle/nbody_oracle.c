@@ -562,12 +562,13 @@ int orc_step(float *block, int n, const orc_params *par,
  * (:534).  Float expressions are kept in the reference's order; -ffp-contract=off matches its PTX (no
  * contraction is possible in these expressions anyway).
  */
-void orc_render(const float *block, int n, unsigned char *img, int width, int height, int field_w, int field_h)
+void orc_render(const float *block, int n, int drawn, unsigned char *img, int width, int height, int field_w, int field_h)
 {
     const float *pos = block, *rad = block + 5 * (size_t)n;
     memset(img, 254, (size_t)width * height);
     const int dfw = field_w << 1, dfh = field_h << 1;                       /* :314-315 */
-    for (int i = 0; i < n; ++i) {
+    /* `drawn`: threads of the launch grid, 128 * floor(n_before_the_step / 128) in the reference's loop (:473,535) */
+    for (int i = 0; i < n && i < drawn; ++i) {
         const float pr = (rad[i] * width) / field_w;                          /* :310 */
         const int cx = (int)(((pos[2 * i] + field_w) / dfw) * width);         /* :318 */
         const int cy = (int)(((pos[2 * i + 1] + field_h) / dfh) * height);    /* :319 */

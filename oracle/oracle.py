@@ -76,7 +76,7 @@ def lib() -> C.CDLL:
                                fp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
         L.orc_rows_dv_f64.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.POINTER(C.c_int), C.c_int,
                                       C.POINTER(C.c_double)]
-        L.orc_render.argtypes = [fp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_render.argtypes = [fp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_step.argtypes = [fp, C.c_int, C.POINTER(OrcParams), C.c_void_p, C.c_longlong,
                                C.POINTER(C.c_longlong)]
         L.orc_step.restype = C.c_int
@@ -191,10 +191,13 @@ def rows_dv_f64(block: np.ndarray, n: int, par: OrcParams, row_idx) -> np.ndarra
     return out
 
 
-def render(block: np.ndarray, n: int, width: int, height: int, field_w: int, field_h: int) -> np.ndarray:
-    """generateImage (src/nbody.cu:294-348) for the n live bodies: uint8[height, width], background 254, bodies 0."""
+def render(block: np.ndarray, n: int, width: int, height: int, field_w: int, field_h: int, grid_n=None) -> np.ndarray:
+    """generateImage (src/nbody.cu:294-348) for the n live bodies: uint8[height, width], background 254, bodies 0.
+    grid_n: the body count before the step just done -- the reference's loop draws with that step's grid, i.e. only the
+    first 128 * max(1, grid_n // 128) bodies (src/nbody.cu:473,535); None draws all."""
     img = np.zeros((height, width), dtype=np.uint8)
-    lib().orc_render(_fptr(np.ascontiguousarray(block[:6 * n])), n, img.ctypes.data, width, height, field_w, field_h)
+    drawn = n if grid_n is None else 128 * max(1, grid_n // 128)
+    lib().orc_render(_fptr(np.ascontiguousarray(block[:6 * n])), n, drawn, img.ctypes.data, width, height, field_w, field_h)
     return img
 
 

@@ -143,7 +143,7 @@ static void free_all(nb_ctx *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
-    void *ptrs[] = {c->st.absorber, c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
+    void *ptrs[] = {c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
                     c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.facc, c->st.xbuf, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
@@ -158,10 +158,6 @@ int nb_create(nb_ctx **out, const nb_params *params)
         return NB_ERR_INVALID;
     }
     *out = nullptr;
-    if ((params->flags & NB_FLAG_MERGE_CONSERVING) && params->world > 1) {
-        set_err(nullptr, "nb_create: NB_FLAG_MERGE_CONSERVING is single-GPU only");
-        return NB_ERR_INVALID;
-    }
     if (params->n_max <= 0 || params->n_max > (1 << 26) || params->field_w <= 0 || params->field_h <= 0 ||
         (params->coverage != NB_COVERAGE_REFERENCE && params->coverage != NB_COVERAGE_FULL) ||
         (params->world > 1 && (params->rank < 0 || params->rank >= params->world))) {
@@ -241,7 +237,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     // all-pairs coverage (the reference's excluded windows are defined by body index) and is sized in only if the
     // capacity can ever reach the threshold
     sp.sort_min_n = 0;
-    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT) && !sp.merge) {
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT)) {
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (st.cap >= min_n) sp.sort_min_n = min_n;
     }
@@ -251,7 +247,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     sp.sym_min_n = 0;
     sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
     if (const char *e = getenv("NBODY_B200_SYM_ROWS")) sp.sym_rows = atoi(e) == 8 ? 8 : 4;                // tuning only
-    if (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_ONE_SIDED) &&
         ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || world == 1)) {
         const int socc = force_sym_occupancy(sp.sym_rows, &c->sym_regs);
         if (socc > 0) {
@@ -280,7 +276,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.pm, sizeof(float4) * (size_t)st.cap);
     NB_ALLOC(st.vel, sizeof(float2) * (size_t)st.cap);
     NB_ALLOC(st.jt, (size_t)kTileBytes * tiles);
-    NB_ALLOC(st.post, (size_t)world * st.shard_cap * 24);
+    st.post_row_bytes = (params->flags & NB_FLAG_MERGE_CONSERVING) ? 28 : 24;
+    NB_ALLOC(st.post, (size_t)world * st.shard_cap * st.post_row_bytes);
     if (sp.sort_min_n > 0) {
         NB_ALLOC(st.jts, sizeof(float) * kSortedTileFloats * tiles);
         for (int k = 0; k < 2; ++k) {
@@ -307,7 +304,6 @@ int nb_create(nb_ctx **out, const nb_params *params)
     if (st.ev_cap > 0) NB_ALLOC(st.ev, sizeof(EventRec) * (size_t)st.ev_cap);
     NB_ALLOC(st.tile_count, sizeof(int) * ctiles);
     if (sp.merge) {
-        NB_ALLOC(st.absorber, sizeof(int) * (size_t)st.cap);
         NB_ALLOC(st.mhead, sizeof(int) * (size_t)st.cap);
         NB_ALLOC(st.mnext, sizeof(int) * (size_t)st.cap);
     }
@@ -447,7 +443,7 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     NB_CUDA(c, launch_finish(c->st, sp, c->stream));
     if (marks) NB_CUDA(c, cudaEventRecord(marks[2], c->stream));
     if (c->sp.world > 1) {
-        const size_t chunk = (size_t)c->st.shard_cap * 24;
+        const size_t chunk = (size_t)c->st.shard_cap * c->st.post_row_bytes;
         NB_NCCL(c, nccl_api()->AllGather(c->st.post + (size_t)c->sp.rank * chunk, c->st.post, chunk, ncclChar, c->comm, c->stream));
     }
     if (sp.merge) NB_CUDA(c, launch_merge(c->st, sp, c->stream));
@@ -745,11 +741,11 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     // the same rules as nb_create (without the device-dependent parts: occupancy, memory budget)
     sp.merge = (params->flags & NB_FLAG_MERGE_CONSERVING) ? 1 : 0;
     sp.sort_min_n = 0;
-    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT) && !sp.merge) {
+    if (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_NO_SORT)) {
         const int min_n = params->sort_min_n > 0 ? params->sort_min_n : NB_SORT_MIN_N_DEFAULT;
         if (params->n_max >= min_n) sp.sort_min_n = min_n;
     }
-    sp.sym = (params->coverage == NB_COVERAGE_FULL && !sp.merge && !(params->flags & NB_FLAG_ONE_SIDED) &&
+    sp.sym = (params->coverage == NB_COVERAGE_FULL && !(params->flags & NB_FLAG_ONE_SIDED) &&
               ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || sp.world == 1)) ? 1 : 0;
     sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
     sp.sym_grid = (sp.sym_rows == 8 ? 2 : 3) * 148; // the queue granularity rule (sym_lgu) is quoted for a B200

@@ -7,7 +7,8 @@
 //                                              one 1-D TMA bulk copy per tile; the last tile is padded with
 //                                              benign bodies (far away, m = 0, r = 0)
 //   post [world][shard_cap*24 B]               uncompacted post-step rows, one chunk per rank:
-//                                              float4 pm[shard_cap] then float2 vel[shard_cap]  (allgather payload)
+//                                              float4 pm[shard_cap] then float2 vel[shard_cap]  (allgather payload;
+//                                              + int absorber[shard_cap] with the opt-in conserving merge)
 //   fpart[G + iblocks][512] float2             partial force sums, one slab per (force CTA, i-block) segment,
 //                                              summed in CTA order by the finish kernel (deterministic)
 //   head [cap] int, cand[cand_cap] int2{j,next} collision candidates: one global list filled through
@@ -141,13 +142,13 @@ struct DevState {
     int2 *cand;
     EventRec *ev;
     int *tile_count;
-    int *absorber;                // conserving merge: lowest index among a body and its hit partners
-    int *mhead, *mnext;           //                   per-root chains of absorbed bodies
+    int *mhead, *mnext;           // conserving merge: per-root chains of absorbed bodies (by body index)
     StepDesc *desc;
     StepResult *res;
     Counters *ctr;
     int cap;                      // n_max
     int shard_cap;                // rows per rank chunk in `post` (multiple of 512)
+    int post_row_bytes;           // 24, or 28 with the conserving merge (absorber plane)
     int cand_cap;
     int ev_cap;
 };
@@ -165,13 +166,19 @@ __host__ __device__ inline int2 *x_pairs(const DevState &st, int rank)
     return reinterpret_cast<int2 *>(st.xbuf + (size_t)rank * st.x_stride + sizeof(XHeader));
 }
 
+// a rank's chunk of `post`: float4 pm[shard_cap], float2 vel[shard_cap] and -- conserving merge only (post_row_bytes
+// = 28) -- int absorber[shard_cap]: the lowest index among the row's body and its hit partners
 __host__ __device__ inline float4 *post_pm(const DevState &st, int rank)
 {
-    return reinterpret_cast<float4 *>(st.post + (size_t)rank * st.shard_cap * 24);
+    return reinterpret_cast<float4 *>(st.post + (size_t)rank * st.shard_cap * st.post_row_bytes);
 }
 __host__ __device__ inline float2 *post_vel(const DevState &st, int rank)
 {
-    return reinterpret_cast<float2 *>(st.post + (size_t)rank * st.shard_cap * 24 + (size_t)st.shard_cap * 16);
+    return reinterpret_cast<float2 *>(st.post + (size_t)rank * st.shard_cap * st.post_row_bytes + (size_t)st.shard_cap * 16);
+}
+__host__ __device__ inline int *post_abs(const DevState &st, int rank)
+{
+    return reinterpret_cast<int *>(st.post + (size_t)rank * st.shard_cap * st.post_row_bytes + (size_t)st.shard_cap * 24);
 }
 
 // Kernels this library itself has launched (or recorded into a graph being captured) on the calling thread: every

@@ -604,10 +604,11 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
     const int row = d.sorted ? st.sidx[0][slot] : slot;
     float4 *out_pm = post_pm(st, p.world > 1 ? p.rank : 0);
     float2 *out_vel = post_vel(st, p.world > 1 ? p.rank : 0);
+    int *out_abs = post_abs(st, p.world > 1 ? p.rank : 0);
     const float4 b = st.pm[row];
     float2 v = st.vel[row];
     if (slot >= d.row_act_hi) {                   // frozen tail: no thread in either reference kernel
-        if (p.merge) st.absorber[row] = row;
+        if (p.merge) out_abs[local] = row;
         out_pm[local] = b;
         out_vel[local] = v;
         if (b.z == 0.f && p.world <= 1 && !p.merge) atomicAdd(&st.tile_count[row / kCompactTile], 1);
@@ -679,7 +680,7 @@ __device__ __forceinline__ bool finish_row(const DevState &st, const StepParams 
             last_key = best_key;
         }
     }
-    if (p.merge) st.absorber[row] = lowest;
+    if (p.merge) out_abs[local] = lowest;
     // velocity + walls (:250-264), position (:288)
     const float ax = fx * p.grav, ay = fy * p.grav;
     const float dvx = p.dt * ax, dvy = p.dt * ay;
@@ -711,56 +712,6 @@ __global__ void __launch_bounds__(256) finish_kernel(const DevState st, const St
     finish_row(st, p, d, row);
 }
 
-// ------------------------------------------------------------------------------------------------
-// opt-in conserving lowest-index merge (NB_FLAG_MERGE_CONSERVING; not reference behaviour), single GPU,
-// bodies' own order.  finish_kernel left absorber[i]; post rows hold the post-force state of every body.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) merge_link_kernel(const DevState st)
-{
-    const int n = st.desc->n;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int r = i;
-    for (int a = st.absorber[r]; a != r; a = st.absorber[r]) r = a;     // pointers only ever go down: terminates
-    if (r != i) st.mnext[i] = atomicExch(&st.mhead[r], i);             // thread i onto its root's chain
-}
-
-__global__ void __launch_bounds__(256) merge_apply_kernel(const DevState st, const StepParams p)
-{
-    const int n = st.desc->n;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int h = st.mhead[i];
-    if (h < 0) return;                             // not a root with members (members are zeroed by their root)
-    st.mhead[i] = -1;
-    float4 *pm = post_pm(st, 0);
-    float2 *vel = post_vel(st, 0);
-    float4 me = pm[i];
-    const float2 v = vel[i];
-    float M = me.z, Px = me.z * v.x, Py = me.z * v.y;
-    int last = -1;
-    while (true) {                                 // members in ascending index order (the chain is unordered)
-        int k = 0x7fffffff;
-        for (int e = h; e >= 0; e = st.mnext[e])
-            if (e > last && e < k) k = e;
-        if (k == 0x7fffffff) break;
-        const float4 o = pm[k];
-        const float2 ov = vel[k];
-        M += o.z;
-        Px = fmaf(o.z, ov.x, Px);
-        Py = fmaf(o.z, ov.y, Py);
-        me.w = fmaf(p.growth, o.w, me.w);
-        pm[k].z = 0.f;                             // removed by the compaction
-        last = k;
-    }
-    me.z = M;
-    pm[i] = me;
-    vel[i] = make_float2(__fdiv_rn(Px, M), __fdiv_rn(Py, M));
-}
-
-// ------------------------------------------------------------------------------------------------
-// compaction: count, then scatter (+ plan of the next step in the last CTA)
-// ------------------------------------------------------------------------------------------------
 // post rows are stored by slot (= index, or position in the sorted order), rank chunk by rank chunk
 __device__ __forceinline__ int post_slot(const DevState &st, int i) { return st.desc->sorted ? st.sinv[i] : i; }
 __device__ __forceinline__ float4 load_post_pm(const DevState &st, int rpr, int i)
@@ -773,6 +724,69 @@ __device__ __forceinline__ float2 load_post_vel(const DevState &st, int rpr, int
     const int s = post_slot(st, i), rk = s / rpr, loc = s - rk * rpr;
     return post_vel(st, rk)[loc];
 }
+
+// ------------------------------------------------------------------------------------------------
+// opt-in conserving lowest-index merge (NB_FLAG_MERGE_CONSERVING; not reference behaviour).  finish_kernel left, per row,
+// the lowest index among the body and its hit partners next to the post-force state; after the allgather every rank
+// holds all of them and runs the same two kernels over all bodies (deterministic: chains are walked in index order).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_link_kernel(const DevState st)
+{
+    const int n = st.desc->n, rpr = st.desc->rows_per_rank;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto absorber = [&](int b) {
+        const int s = post_slot(st, b), rk = s / rpr;
+        return post_abs(st, rk)[s - rk * rpr];
+    };
+    int r = i;
+    for (int a = absorber(r); a != r; a = absorber(r)) r = a;          // pointers only ever go down: terminates
+    if (r != i) st.mnext[i] = atomicExch(&st.mhead[r], i);             // thread i onto its root's chain
+}
+
+__global__ void __launch_bounds__(256) merge_apply_kernel(const DevState st, const StepParams p)
+{
+    const int n = st.desc->n, rpr = st.desc->rows_per_rank;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int h = st.mhead[i];
+    if (h < 0) return;                             // not a root with members (members are zeroed by their root)
+    st.mhead[i] = -1;
+    auto pm_of = [&](int b) {
+        const int s = post_slot(st, b), rk = s / rpr;
+        return post_pm(st, rk) + (s - rk * rpr);
+    };
+    auto vel_of = [&](int b) {
+        const int s = post_slot(st, b), rk = s / rpr;
+        return post_vel(st, rk) + (s - rk * rpr);
+    };
+    float4 me = *pm_of(i);
+    const float2 v = *vel_of(i);
+    float M = me.z, Px = me.z * v.x, Py = me.z * v.y;
+    int last = -1;
+    while (true) {                                 // members in ascending index order (the chain is unordered)
+        int k = 0x7fffffff;
+        for (int e = h; e >= 0; e = st.mnext[e])
+            if (e > last && e < k) k = e;
+        if (k == 0x7fffffff) break;
+        float4 *ok = pm_of(k);
+        const float4 o = *ok;
+        const float2 ov = *vel_of(k);
+        M += o.z;
+        Px = fmaf(o.z, ov.x, Px);
+        Py = fmaf(o.z, ov.y, Py);
+        me.w = fmaf(p.growth, o.w, me.w);
+        ok->z = 0.f;                               // removed by the compaction
+        last = k;
+    }
+    me.z = M;
+    *pm_of(i) = me;
+    *vel_of(i) = make_float2(__fdiv_rn(Px, M), __fdiv_rn(Py, M));
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction: count, then scatter (+ plan of the next step in the last CTA)
+// ------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kCompactThreads) count_kernel(const DevState st, const StepParams p)
 {

@@ -65,13 +65,15 @@ def _worker(rank: int, world: int, port: int, n0: int, field: int, coverage: int
 # kernel (blocks of the pair triangle dealt to the ranks, exchange of partial forces and candidate pairs)
 @pytest.mark.parametrize("n0,field,coverage,sort_min_n,flags", [(16384, 100000, 0, 0, 0), (16384, 100000, 1, 0, 0), (3000, 12000, 1, 0, 0),
                                                                (700, 3000, 0, 0, 0), (16384, 100000, 1, 1024, 0), (3000, 12000, 1, 2900, 0),
-                                                               (16384, 100000, 1, 1024, 32), (20000, 30000, 1, 1024, 0)])
+                                                               (16384, 100000, 1, 1024, 32), (20000, 30000, 1, 1024, 0),
+                                                               # flags 16 = NB_FLAG_MERGE_CONSERVING: the opt-in merge, sharded
+                                                               (3000, 12000, 1, 0, 16), (20000, 30000, 1, 1024, 16)])
 def test_two_gpus_match_oracle(oracle, nb, tmp_path, n0, field, coverage, sort_min_n, flags):
     import torch.multiprocessing as mp
     world, steps = 2, 4
     mp.spawn(_worker, args=(world, _free_port(), n0, field, coverage, steps, str(tmp_path), sort_min_n, flags), nprocs=world, join=True)
     block = nb.generate(nb.SCENARIO_SQUARE, n0, field_w=field, field_h=field)
-    par = oracle.params(field_w=field, field_h=field, coverage=coverage)
+    par = oracle.params(field_w=field, field_h=field, coverage=coverage, merge=1 if flags & 16 else 0)
     n = n0
     ranks = [np.load(tmp_path / f"rank_{r}.npz") for r in range(world)]
     ev_all = np.concatenate([np.load(tmp_path / f"events_{r}.npy") for r in range(world)])

@@ -152,5 +152,5 @@ def test_render_restatement_matches_the_reference_images(oracle, golden_dir):
         n = sc["n"]
         for _ in range(sc["steps"]):
             n, _, _ = oracle.step(block, n, par)
-        img = oracle.render(block, min(n, sc["drawn"]), sc["width"], sc["height"], sc["field"], sc["field"])
+        img = oracle.render(block, n, sc["width"], sc["height"], sc["field"], sc["field"], grid_n=sc["grid_n"])
         assert f"{oracle.fnv(img):016x}" == sc["fnv"] and int((img == 0).sum()) == sc["body_pixels"], name

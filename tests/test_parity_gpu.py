@@ -217,6 +217,40 @@ def test_rows_at_131072(nb, oracle):
     assert err_gpu <= max(err_ref, 2e-6)
 
 
+def test_cluster_131072_four_steps_against_the_oracle(nb, oracle):
+    """BASELINE configs[2] at its full size (cold disc R = 1e5 in a +-2e5 field: every second body collides in the first
+    step), four free-running steps, every one compared with a full oracle step: events in visit order, survivors,
+    masses and radii bit-exact, trajectories within the free-running tolerances.  The steps after the first run on a
+    re-sorted, re-planned order with tens of thousands of bodies removed -- what a one-step test never sees."""
+    n, field = 131072, 200000
+    block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5, field_w=field, field_h=field)
+    st = _run_side_by_side(nb, oracle, block0, n, 4, nb.COVERAGE_FULL, field)
+    assert st["pair_halving"] == 1 and st["culled_parts"] > 0 and st["n"] < 80000
+
+
+@pytest.mark.parametrize("config,checkpoints", [("disc1m", (5, 10, 20)), ("cluster", (2, 8, 30))])
+def test_resynchronised_rows_after_compactions(nb, oracle, config, checkpoints):
+    """BASELINE configs[3] (N = 1 048 576) and [2] deep into the run: at steps 5 / 10 / 20 the CUDA state is downloaded,
+    the oracle evaluates a sample of its rows (random rows + rows with collisions) from that very state, and the next
+    CUDA step must reproduce them: events per row, survivors, masses and radii bit-exact, positions within 1e-5 of the
+    field, velocity changes within 1e-5 of a float64 evaluation (or the oracle's own float32 error).  This is the
+    comparison bench.py prints as `parity`; here it runs after many compactions, re-sorts and re-plans."""
+    import bench
+    cfg = dict(bench.CONFIGS[config])
+    block0 = bench.make_block(nb, cfg, product=True)
+    sim = nb.Simulation(cfg["n"], field_w=cfg["field"], field_h=cfg["field"], coverage=nb.COVERAGE_FULL, event_capacity=1 << 22)
+    sim.upload(block0, cfg["n"])
+    done = 0
+    for cp in checkpoints:
+        sim.step(cp - done)
+        res = bench.parity_one_gpu(nb, sim, cfg, n_rows=256)
+        done = cp + 1                                   # the check itself advanced one step
+        assert res["checked"] and res["ok"], (config, cp, res)
+        assert res["dp_max_over_field"] <= POS_TOL and res["dv_err_vs_f64"] <= max(1e-5, res["dv_err_oracle_vs_f64"])
+    assert sim.stats()["overflow"] == 0
+    sim.close()
+
+
 def _force_error_vs_f64(nb, oracle, block0, n, field, coverage):
     """max |dv - dv_f64| / max |dv_f64| over all surviving rows, for the CUDA path and for the oracle
     (= the reference's float32 arithmetic), after one step from rest (v = 0, so v' = dv)."""
@@ -344,7 +378,7 @@ def test_drop_in_driver(nb, oracle, tmp_path):
         if s == 1:
             first = (tmp_path / "imgs" / "iteration_0.ppm").read_bytes()
             # like the reference, the driver draws with the grid of the step it has just done: 128 * floor(300 / 128) bodies
-            assert first == b"P5\n64 48\n255\n" + oracle.render(block, min(n, 256), 64, 48, 2000, 2000).tobytes()
+            assert first == b"P5\n64 48\n255\n" + oracle.render(block, n, 64, 48, 2000, 2000, grid_n=300).tobytes()
         n, _, ev = oracle.step(block, n, par, want_events=True)
         ev_rows += [f"{s},{e['i']},{e['j']},{e['kind']}" for e in ev]
     raw = (tmp_path / "state.bin").read_bytes()
@@ -550,14 +584,18 @@ def test_opt_in_plummer_softening(nb, oracle, n, field, coverage, sort_min_n):
     assert soft["steps"] == hard["steps"] == 5
 
 
-@pytest.mark.parametrize("n,field,coverage,steps", [(300, 1500, 1, 4), (3000, 12000, 1, 6), (3000, 12000, 0, 6), (16384, 100000, 1, 8),
-                                                    (16384, 35000, 1, 3)])
-def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps):
+@pytest.mark.parametrize("n,field,coverage,steps,sort_min_n", [(300, 1500, 1, 4, 0), (3000, 12000, 1, 6, 0), (3000, 12000, 0, 6, 0),
+                                                               (16384, 100000, 1, 8, 0), (16384, 35000, 1, 3, 0),
+                                                               (5000, 20000, 1, 5, 1024), (16384, 35000, 1, 3, 1024)])
+def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps, sort_min_n):
     """Opt-in physics beyond parity (the north star's wording): lowest-index merge that conserves
     mass and momentum.  Against the oracle's restatement of the same rule: events, survivors, masses and radii
-    bit-exact; and the conservation laws themselves on the CUDA result."""
+    bit-exact; and the conservation laws themselves on the CUDA result.  It runs on every force path: one-sided
+    (reference coverage, small n), two-sided on the bodies' own order (n = 16384) and on the cell-sorted order
+    (sort_min_n forced down)."""
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
-    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=coverage, event_capacity=64 * n, flags=nb.FLAG_MERGE_CONSERVING)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=coverage, event_capacity=64 * n, flags=nb.FLAG_MERGE_CONSERVING,
+                        sort_min_n=sort_min_n)
     sim.upload(block0, n)
     cpu, n_cpu = block0.copy(), n
     par = oracle.params(field_w=field, field_h=field, coverage=coverage, merge=1)
@@ -579,6 +617,6 @@ def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps):
         p_after = (mg.astype(np.float64)[:, None] * vg.astype(np.float64)).sum(axis=0)
         assert (np.abs(p_after - mv.sum(axis=0)) <= 1e-5 * np.abs(mv).sum(axis=0) + 1e-30).all(), f"step {s}: momentum not conserved"
     assert merged_any
+    st = sim.stats()
+    assert st["pair_halving"] == (1 if coverage == 1 and (sort_min_n > 0 or st["n"] >= 6144) and st["n"] >= 1024 else 0)
     sim.close()
-    with pytest.raises(nb.NbodyError):
-        nb.Simulation(n, field_w=field, field_h=field, flags=nb.FLAG_MERGE_CONSERVING, world=2, rank=0)

@@ -154,7 +154,7 @@ def test_two_sided_plan_flags(nb):
     p = nb.plan(30000, n_max=131072)                                  # a big context whose body count has dropped
     assert p["sorted"] == 0 and p["two_sided"] == 1 and p["sym_lgu"] >= 1
     assert nb.plan(30000, n_max=131072, world=2)["two_sided"] == 0 and nb.plan(5000, n_max=131072)["two_sided"] == 0
-    assert nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["sorted"] == 0
+    assert nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["sorted"] == 1 and nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["two_sided"] == 1
     with pytest.raises(nb.NbodyError):
         nb.plan_block(4, 10)
 

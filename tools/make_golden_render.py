@@ -52,11 +52,11 @@ def main():
         img = ref.render(w, h, field, field, grid_n)
         ref.close()
         drawn = 128 * max(1, grid_n // 128)
-        mine = O.render(cpu, min(n_cpu, drawn), w, h, field, field)
+        mine = O.render(cpu, n_cpu, w, h, field, field, grid_n=grid_n)
         ok = bool(np.array_equal(img, mine))
         all_ok &= ok
         golden["scenarios"][name] = {"n": n, "field": field, "min_radius": rmin, "max_radius": rmax, "width": w, "height": h,
-                                     "steps": steps, "drawn": min(n, drawn), "fnv": f"{O.fnv(img):016x}",
+                                     "steps": steps, "grid_n": grid_n, "drawn": min(n, drawn), "fnv": f"{O.fnv(img):016x}",
                                      "body_pixels": int((img == 0).sum()), "oracle_byte_exact": ok}
         print(f"[{name}] {w}x{h} drawn {min(n, drawn)}/{n} body pixels {int((img == 0).sum())} oracle_byte_exact={ok}", flush=True)
         if not ok:
