@@ -255,7 +255,11 @@ int nb_create(nb_ctx **out, const nb_params *params)
             sp.sym_grid = c->sm_count * socc;
             if (world == 1) {
                 sp.sym_min_n = kSymMinNDefault;
+                sp.sym_small = 2;
                 if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);       // tuning only
+                if (const char *e = getenv("NBODY_B200_SYM_SMALL")) sp.sym_small = atoi(e) == 1 ? 1 : 2;
+                int wregs = 0;
+                sp.symw_grid = c->sm_count * std::max(1, force_symw_occupancy(&wregs));
             }
         }
     }
@@ -310,7 +314,7 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.desc, sizeof(StepDesc));
     NB_ALLOC(st.res, sizeof(StepResult));
     NB_ALLOC(st.ctr, sizeof(Counters));
-    NB_ALLOC(c->dev_block, (size_t)24 * st.cap);
+    NB_ALLOC(c->dev_block, (size_t)24 * (st.cap + 4 * world));      // room for the padded arrays of a sharded upload
 #undef NB_ALLOC
     c->sp_plain = sp;
     c->sp_plain.sort_min_n = 0;
@@ -353,11 +357,38 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
     NB_CUDA(c, cudaStreamSynchronize(c->stream));
     LaunchScope scope(c);
     c->ring_pos = 0;
-    if (n > 0) NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
+    const float *host = static_cast<const float *>(bodies);
+    float *dev = static_cast<float *>(c->dev_block);
+    const float *d_pos = dev, *d_vel = dev + 2 * (size_t)n, *d_mass = dev + 4 * (size_t)n, *d_rad = dev + 5 * (size_t)n;
+    if (c->sp.world > 1 && c->comm_ready && n >= 4 * c->sp.world) {
+        // sharded upload: every rank holds the same host block, so each copies only its 1 / world of every array over
+        // PCIe and the rest arrives from the peers over NVLink (four in-place allgathers into arrays padded to world
+        // equal chunks)
+        const int W = c->sp.world, r = c->sp.rank;
+        const size_t chunk = (((size_t)n + W - 1) / W + 3) / 4 * 4, padded = chunk * W;
+        const size_t lo = std::min<size_t>((size_t)r * chunk, (size_t)n), hi = std::min<size_t>(lo + chunk, (size_t)n);
+        float *p_pos = dev, *p_vel = dev + 2 * padded, *p_mass = dev + 4 * padded, *p_rad = dev + 5 * padded;
+        if (hi > lo) {
+            NB_CUDA(c, cudaMemcpyAsync(p_pos + 2 * lo, host + 2 * lo, 8 * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+            NB_CUDA(c, cudaMemcpyAsync(p_vel + 2 * lo, host + 2 * (size_t)n + 2 * lo, 8 * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+            NB_CUDA(c, cudaMemcpyAsync(p_mass + lo, host + 4 * (size_t)n + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+            NB_CUDA(c, cudaMemcpyAsync(p_rad + lo, host + 5 * (size_t)n + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+        }
+        NB_NCCL(c, nccl_api()->AllGather(p_pos + 2 * r * chunk, p_pos, 8 * chunk, ncclChar, c->comm, c->stream));
+        NB_NCCL(c, nccl_api()->AllGather(p_vel + 2 * r * chunk, p_vel, 8 * chunk, ncclChar, c->comm, c->stream));
+        NB_NCCL(c, nccl_api()->AllGather(p_mass + r * chunk, p_mass, 4 * chunk, ncclChar, c->comm, c->stream));
+        NB_NCCL(c, nccl_api()->AllGather(p_rad + r * chunk, p_rad, 4 * chunk, ncclChar, c->comm, c->stream));
+        d_pos = p_pos;
+        d_vel = p_vel;
+        d_mass = p_mass;
+        d_rad = p_rad;
+    } else if (n > 0) {
+        NB_CUDA(c, cudaMemcpyAsync(c->dev_block, bodies, (size_t)24 * n, cudaMemcpyHostToDevice, c->stream));
+    }
     NB_CUDA(c, cudaMemsetAsync(c->st.res, 0, sizeof(StepResult), c->stream));
     NB_CUDA(c, cudaMemsetAsync(c->st.tile_count, 0, sizeof(int) * ((size_t)(c->st.cap + kCompactTile - 1) / kCompactTile), c->stream));
     if (c->st.facc) NB_CUDA(c, cudaMemsetAsync(c->st.facc, 0, sizeof(long long) * 2 * c->st.slots, c->stream));
-    NB_CUDA(c, launch_ingest(c->st, (const float *)c->dev_block, n, c->stream));
+    NB_CUDA(c, launch_ingest(c->st, d_pos, d_vel, d_mass, d_rad, n, c->stream));
     NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
     if (c->sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, c->sp, c->stream));
     // the caller may reuse `bodies` as soon as we return
@@ -621,7 +652,7 @@ int nb_get_stats(nb_ctx *c, nb_stats *out)
     out->force_regs = c->force_regs;
     out->force_threads = c->force_threads;
     out->force_variant = c->variant;
-    out->pair_halving = d.sym;
+    out->pair_halving = d.sym != 0 ? 1 : 0;
     out->sym_regs = c->sp.sym ? c->sym_regs : 0;
     out->row_lo = d.row_lo;
     out->row_hi = d.row_hi;
@@ -750,6 +781,8 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
     sp.sym_grid = (sp.sym_rows == 8 ? 2 : 3) * 148; // the queue granularity rule (sym_lgu) is quoted for a B200
     sp.sym_min_n = sp.world == 1 ? kSymMinNDefault : 0;
+    sp.sym_small = 2;
+    sp.symw_grid = 6 * 148;
     sp.field_w = sp.field_h = 1;
     {
         int variant = (params->flags >> NB_FLAG_VARIANT_SHIFT) & 0xf;
@@ -773,7 +806,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     out->n_jtiles = d.n_jtiles;
     out->units = d.units;
     out->sorted = d.sorted;
-    out->two_sided = d.sym;
+    out->two_sided = d.sym != 0 ? 1 : 0;
     out->sym_S = d.sym_S;
     out->sym_Q = d.sym_Q;
     out->sym_blocks = d.sym_blocks;

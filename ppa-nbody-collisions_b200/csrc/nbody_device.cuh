@@ -40,7 +40,9 @@ constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
 constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
 constexpr int kSymSMax = 8;                  // two-sided force kernel: a block of the pair triangle is S x S tile pairs, S <= 8
-constexpr int kSymMinNDefault = 6144;        // smallest n the two-sided kernel takes on the bodies' own order (one GPU)
+constexpr int kSymMinNDefault = 1024;        // smallest n the two-sided kernel takes on the bodies' own order (one GPU)
+constexpr int kWGroup = 128;                 // warp-level two-sided kernel (nbody_symw.cu): rows per group, bodies per chunk
+constexpr int kWChunk = 64;
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
 constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
 
@@ -60,9 +62,10 @@ struct StepDesc {                 // rewritten on the device at the end of every
     int force_exact;              // 1: every sub-chunk takes the exact path (n < 256)
     int lg_parts;                 // a work unit is kTJ >> lg_parts bodies of one j-tile (0 .. kMaxLgParts)
     int sorted;                   // 1: the force kernel streams the cell-sorted j-tiles (jts) this step
-    int sym;                      // 1: this step runs the two-sided (pair-halving) force kernel (on the sorted order when
-                                  //    `sorted`, else on the bodies' own order)
-    int sym_S, sym_Q;             //    tiles per super-tile, super-tiles (Q = ceil(T / S))
+    int sym;                      // this step's force kernel: 0 one-sided; 1 two-sided, a CTA per tile pair (nbody_sym.cu: on the
+                                  //    sorted order when `sorted`); 2 two-sided, a warp per work item (nbody_symw.cu: small n,
+                                  //    bodies' own order, one GPU)
+    int sym_S, sym_Q;             //    1: tiles per super-tile, super-tiles (Q = ceil(T / S));  2: sym_S = chunks per work item
     int sym_blocks;               //    Q (Q + 1) / 2 blocks of the pair triangle
     int sym_lgu;                  //    a tile pair is split into 1 << sym_lgu work items of 4 >> sym_lgu rounds (S == 1 only)
     int sym_items;                //    sym_blocks << sym_lgu items in the work queue
@@ -115,6 +118,8 @@ struct StepParams {
     int sym;                      // 1: steps on the cell-sorted order evaluate each unordered pair once (two-sided kernel)
     int sym_grid;                 //    its grid (resident CTAs x SMs)
     int sym_min_n;                //    smallest n that runs it on the bodies' own order (one GPU); sorted steps always do
+    int sym_small;                //    which kernel takes those steps: 2 the warp-level one (default), 1 the CTA-level one
+    int symw_grid;                //    grid of the warp-level kernel (CTAs of 128 threads)
     int sym_rows;                 //    rows per lane: 4 (default), 8 (NB_FLAG_SYM_ROWS8)
 };
 
@@ -186,17 +191,48 @@ __host__ __device__ inline int *post_abs(const DevState &st, int rank)
 long long &launch_counter();
 inline void count_launch(int k = 1) { launch_counter() += k; }
 
+
+// ---- warp-level two-sided kernel: its work queue (shared with the plan) ------------------------------------------
+// Queue ids -> (group, first chunk slot).  Group g needs the chunk slots s0(g) = floor(2 g / run) .. S - 1; pairing g
+// with G - 1 - g makes (almost) equal-length rows of L ids each, so an id decodes with one division; ids that fall off
+// the end of a row pair are void (at most one per row).
+struct WGeom {
+    int G, C, S, run, L, ids;
+};
+__host__ __device__ inline WGeom symw_geom(int n, int run)
+{
+    WGeom w;
+    w.G = (n + kWGroup - 1) / kWGroup;
+    w.C = (n + kWChunk - 1) / kWChunk;
+    w.run = run;
+    w.S = (w.C + run - 1) / run;
+    w.L = 2 * w.S - (2 * w.G - 2) / run + (run > 2 ? 1 : 0);     // run <= 2: the two floors are exact
+    w.ids = ((w.G + 1) / 2) * w.L;
+    return w;
+}
+// chunks per work item for n bodies on `warps` resident warps: the longest run that still leaves >= 12 items per warp
+__host__ __device__ inline int symw_run(int n, int warps)
+{
+    int run = 8;
+    while (run > 1 && symw_geom(n, run).ids < 12 * warps) run >>= 1;
+    return run;
+}
+
 // kernels (nbody_kernels.cu)
 cudaError_t launch_plan(const DevState &st, const StepParams &p, int n, cudaStream_t s);
 cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, cudaStream_t s);
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_force_sym(const DevState &st, const StepParams &p, cudaStream_t s);    // nbody_sym.cu
+cudaError_t launch_force_symw(const DevState &st, const StepParams &p, cudaStream_t s);   // nbody_symw.cu
+int force_symw_occupancy(int *regs);
 cudaError_t launch_sym_chain(const DevState &st, const StepParams &p, cudaStream_t s);    // sharded two-sided kernel: after the allgather of xbuf
 cudaError_t launch_compact(const DevState &st, const StepParams &p, bool recount, cudaStream_t s);
 cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s);
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s);      // nbody_sort.cu
 size_t sort_hist_entries(int cap);
-cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s);
+// the four arrays of a BodiesData block (src/nbody.cu:66-77), wherever they lie on the device
+cudaError_t launch_ingest(const DevState &st, const float *pos, const float *vel, const float *mass, const float *rad, int n,
+                          cudaStream_t s);
 cudaError_t launch_export(const DevState &st, float *block, int n, cudaStream_t s);
 cudaError_t launch_render(const DevState &st, int n, unsigned char *img, int w, int h, int field_w, int field_h,
                           cudaStream_t s);

@@ -73,8 +73,14 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.finv = 1.0;
     // Two-sided kernel: always on the cell-sorted order; on the bodies' own order (every round pre-tested) from sym_min_n
     // bodies on, one GPU only.  It needs a fixed-point scale for its force sums; without one the one-sided kernel runs.
-    const bool sym_size = d.sorted || (p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n && n >= 2 * kTJ);
-    if (p.sym && p.coverage == NB_COVERAGE_FULL && sym_size &&
+    const bool small = !d.sorted && p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n;
+    if (p.sym && p.coverage == NB_COVERAGE_FULL && small && p.sym_small == 2 &&
+        sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
+        // below the sort threshold: a warp per work item (nbody_symw.cu)
+        d.sym = 2;
+        d.sym_S = symw_run(n, 4 * (p.symw_grid > 0 ? p.symw_grid : 1));
+        d.sym_items = symw_geom(n, d.sym_S).ids;
+    } else if (p.sym && p.coverage == NB_COVERAGE_FULL && (d.sorted || (small && p.sym_small == 1 && n >= 2 * kTJ)) &&
         sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
         // the triangle of tile pairs in blocks of S x S; S depends on the tile count alone, so that one GPU and several
         // cut the work -- and round the partial sums -- alike: their results agree bit for bit
@@ -939,16 +945,18 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
 // ------------------------------------------------------------------------------------------------
 // ingest / export: the reference's BodiesData block (src/nbody.cu:66-77) <-> the SoA store
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ingest_kernel(const DevState st, const float *__restrict__ block, const int n)
+__global__ void __launch_bounds__(256) ingest_kernel(const DevState st, const float2 *__restrict__ pos_in,
+                                                     const float2 *__restrict__ vel_in, const float *__restrict__ mass_in,
+                                                     const float *__restrict__ rad_in, const int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pad_end = (n + kTJ - 1) / kTJ * kTJ;
     float r = 0.f, mx = 0.f, rn = __int_as_float(0x7f800000);
     if (i < n) {
-        const float2 pos = reinterpret_cast<const float2 *>(block)[i];
-        const float2 v = reinterpret_cast<const float2 *>(block + 2 * (size_t)n)[i];
-        const float m = block[4 * (size_t)n + i];
-        r = block[5 * (size_t)n + i];
+        const float2 pos = pos_in[i];
+        const float2 v = vel_in[i];
+        const float m = mass_in[i];
+        r = rad_in[i];
         mx = m;
         rn = r;
         store_body(st, i, make_float4(pos.x, pos.y, m, r), v);
@@ -1057,8 +1065,10 @@ cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, c
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !p.sym) return e;
-    // a context that can run the two-sided kernel: whichever kernel the step descriptor does not name returns at once
-    return launch_force_sym(st, p, s);
+    // a context that can run the two-sided kernels: whichever kernel the step descriptor does not name returns at once
+    if (p.sort_min_n > 0 || p.sym_small == 1) e = launch_force_sym(st, p, s);
+    if (e == cudaSuccess && p.sym_small == 2 && p.sym_min_n > 0) e = launch_force_symw(st, p, s);
+    return e;
 }
 
 cudaError_t launch_finish(const DevState &st, const StepParams &p, cudaStream_t s)
@@ -1093,10 +1103,12 @@ cudaError_t launch_merge(const DevState &st, const StepParams &p, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_ingest(const DevState &st, const float *block, int n, cudaStream_t s)
+cudaError_t launch_ingest(const DevState &st, const float *pos, const float *vel, const float *mass, const float *rad, int n,
+                          cudaStream_t s)
 {
     const int span = st.cap + kTJ;
-    ingest_kernel<<<(span + 255) / 256, 256, 0, s>>>(st, block, n);
+    ingest_kernel<<<(span + 255) / 256, 256, 0, s>>>(st, reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel),
+                                                     mass, rad, n);
     count_launch();
     return cudaGetLastError();
 }

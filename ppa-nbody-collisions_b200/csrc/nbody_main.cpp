@@ -22,13 +22,19 @@
 //   --resume PATH        start from a --dump-state file instead of generating initial conditions
 //                        (checkpoint / resume: the reference has none)
 //   --dump-events PATH   write the collision event list as CSV (step,i,j,kind)
-//   --device D           CUDA device ordinal
+//   --device D           CUDA device ordinal (of rank 0 with --gpus)
+//   --gpus N             shard the step over N GPUs of this node: one host thread and one library context per GPU
+//                        (devices D .. D + N - 1), NCCL between them (nb_comm_unique_id / nb_comm_init).  Rank 0 prints,
+//                        draws and dumps; the event list is merged from all ranks.  Results do not depend on N for the
+//                        two-sided kernel (all-pairs coverage from 40960 bodies on): its force sums are exact integers
 #include <sys/time.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nbody_b200.h"
@@ -50,7 +56,7 @@ int main(int argc, char **argv)
 {
     const double start = now_s();
     std::string config_path = "nbodyConfig.txt", dump_state, dump_events, resume, scenario = "square";
-    int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0;
+    int coverage = NB_COVERAGE_REFERENCE, steps_override = -1, device = 0, gpus = 1;
     unsigned long long seed = 1024;
     double extent = 0, softening = 0;
     bool images = true, conserving = false, one_sided = false, render_all = false;
@@ -83,6 +89,7 @@ int main(int argc, char **argv)
         else if (opt == "--dump-events") dump_events = need("--dump-events");
         else if (opt == "--resume") resume = need("--resume");
         else if (opt == "--device") device = atoi(need("--device"));
+        else if (opt == "--gpus") gpus = atoi(need("--gpus"));
         else { fprintf(stderr, "unknown option %s\n", opt.c_str()); return 2; }
     }
 
@@ -132,76 +139,107 @@ int main(int argc, char **argv)
         return 1;
     }
 
-    nb_params par;
-    memset(&par, 0, sizeof(par));
-    par.n_max = n0;
-    par.dt = cfg.timestep;
-    par.growth = cfg.growthRate;
-    par.field_w = cfg.fieldWidth;
-    par.field_h = cfg.fieldHeight;
-    par.coverage = coverage;
-    par.device = device;
-    par.softening = (float)softening;
-    if (conserving) par.flags |= NB_FLAG_MERGE_CONSERVING;
-    if (one_sided) par.flags |= NB_FLAG_ONE_SIDED;
-    par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
-    nb_ctx *ctx = nullptr;
-    int rc = nb_create(&ctx, &par);
-    if (rc != NB_OK) die(nullptr, "nb_create", rc);
-    if ((rc = nb_upload(ctx, block.data(), n0)) != NB_OK) die(ctx, "nb_upload", rc);
+    if (gpus < 1) gpus = 1;
+    unsigned char comm_id[NB_UNIQUE_ID_BYTES];
+    if (gpus > 1) {
+        const int rc = nb_comm_unique_id(comm_id);
+        if (rc != NB_OK) die(nullptr, "nb_comm_unique_id", rc);
+    }
+    const bool do_images = images && every > 0 && cfg.imgWidth > 0 && cfg.imgHeight > 0;
+    std::vector<std::vector<nb_event>> events(gpus);       // per rank: the rows it finished
 
-    FILE *evf = nullptr;
+    // One rank = one GPU = one library context, driven by its own host thread.  Every rank makes the same calls (the
+    // collectives inside nb_step keep them in step); rank 0 alone talks to the outside world.
+    auto run_rank = [&](const int rank) {
+        nb_params par;
+        memset(&par, 0, sizeof(par));
+        par.n_max = n0;
+        par.dt = cfg.timestep;
+        par.growth = cfg.growthRate;
+        par.field_w = cfg.fieldWidth;
+        par.field_h = cfg.fieldHeight;
+        par.coverage = coverage;
+        par.device = device + rank;
+        par.rank = rank;
+        par.world = gpus;
+        par.softening = (float)softening;
+        if (conserving) par.flags |= NB_FLAG_MERGE_CONSERVING;
+        if (one_sided) par.flags |= NB_FLAG_ONE_SIDED;
+        par.event_capacity = dump_events.empty() ? 0 : 1 << 22;
+        nb_ctx *ctx = nullptr;
+        int rc = nb_create(&ctx, &par);
+        if (rc != NB_OK) die(nullptr, "nb_create", rc);
+        if (gpus > 1 && (rc = nb_comm_init(ctx, comm_id)) != NB_OK) die(ctx, "nb_comm_init", rc);
+        if ((rc = nb_upload(ctx, block.data(), n0)) != NB_OK) die(ctx, "nb_upload", rc);
+
+        const bool lead = rank == 0;
+        const bool want_events = !dump_events.empty();
+        std::vector<nb_event> evbuf(want_events ? (1 << 22) : 0);
+        std::vector<uint8_t> img(lead && do_images ? (size_t)cfg.imgWidth * cfg.imgHeight : 0);
+        int pending = -1;                               // iteration whose image waits to be saved
+        for (int it = 0; it < total; ++it) {
+            int n_before = 0;                           // the reference draws with the grid of the step it has just done
+            if (lead && do_images && it % every == 0 && !render_all && (rc = nb_num_bodies(ctx, &n_before)) != NB_OK)
+                die(ctx, "nb_num_bodies", rc);
+            if ((rc = nb_step(ctx, 1)) != NB_OK) die(ctx, "nb_step", rc);
+            if (lead && do_images) {
+                // the image rendered after iteration k is written during iteration k + 1 (:513-522)
+                if (pending >= 0 && (it - 1) % every == 0) {
+                    const std::string path = std::string(cfg.imagePath) + "/iteration_" + std::to_string(pending) + ".ppm";
+                    printf("Saving (%dx%d) to disk\n", cfg.imgWidth, cfg.imgHeight);  // :356
+                    fflush(stdout);
+                    if (nb_write_pgm(path.c_str(), img.data(), cfg.imgWidth, cfg.imgHeight) != NB_OK) {
+                        fprintf(stderr, "Error writing image to file:%s\nEnsure the the folder exists\n", path.c_str());   // :365-369
+                        exit(1);
+                    }
+                    pending = -1;
+                }
+                if (it % every == 0) {                  // :529-539
+                    const int grid = render_all ? 0x7fffffff : 128 * (n_before < 128 ? 1 : n_before / 128);              // :473,535
+                    if ((rc = nb_render_grid(ctx, img.data(), cfg.imgWidth, cfg.imgHeight, grid)) != NB_OK) die(ctx, "nb_render", rc);
+                    pending = it;
+                }
+            }
+            if (want_events && (it % 64 == 63 || it == total - 1)) {
+                int cnt = 0;
+                if ((rc = nb_events(ctx, evbuf.data(), (int)evbuf.size(), &cnt)) != NB_OK) die(ctx, "nb_events", rc);
+                events[rank].insert(events[rank].end(), evbuf.begin(), evbuf.begin() + cnt);
+            }
+        }
+        if ((rc = nb_sync(ctx)) != NB_OK) die(ctx, "nb_sync", rc);                // CUDA_SYNC_CHECK, :546
+        if (lead && !dump_state.empty()) {
+            int n = 0;
+            if ((rc = nb_download(ctx, block.data(), n0, &n)) != NB_OK) die(ctx, "nb_download", rc);
+            FILE *f = fopen(dump_state.c_str(), "wb");
+            if (!f) { fprintf(stderr, "cannot open %s\n", dump_state.c_str()); exit(1); }
+            const int32_t n32 = n;
+            fwrite(&n32, sizeof(n32), 1, f);
+            fwrite(block.data(), 24, (size_t)n, f);
+            fclose(f);
+        }
+        nb_destroy(ctx);
+    };
+    if (gpus == 1) {
+        run_rank(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int r = 0; r < gpus; ++r) threads.emplace_back(run_rank, r);
+        for (std::thread &t : threads) t.join();
+    }
     if (!dump_events.empty()) {
-        evf = fopen(dump_events.c_str(), "w");
+        // every rank's list is sorted by (step, row, visit order) and the ranks finish disjoint rows: a stable sort of
+        // the concatenation by (step, row) is the single-GPU list
+        std::vector<nb_event> all;
+        for (const auto &e : events) all.insert(all.end(), e.begin(), e.end());
+        std::stable_sort(all.begin(), all.end(), [](const nb_event &a, const nb_event &b) {
+            return a.step != b.step ? a.step < b.step : a.i < b.i;
+        });
+        FILE *evf = fopen(dump_events.c_str(), "w");
         if (!evf) { fprintf(stderr, "cannot open %s\n", dump_events.c_str()); return 1; }
         fputs("step,i,j,kind\n", evf);
+        for (const nb_event &e : all) fprintf(evf, "%d,%d,%d,%d\n", e.step, e.i, e.j, e.kind);
+        fclose(evf);
     }
-    std::vector<nb_event> evbuf(evf ? (1 << 22) : 0);
-    const bool do_images = images && every > 0 && cfg.imgWidth > 0 && cfg.imgHeight > 0;
-    std::vector<uint8_t> img(do_images ? (size_t)cfg.imgWidth * cfg.imgHeight : 0);
-    int pending = -1;                               // iteration whose image waits to be saved
-    for (int it = 0; it < total; ++it) {
-        int n_before = 0;                           // the reference draws with the grid of the step it has just done
-        if (do_images && it % every == 0 && !render_all && (rc = nb_num_bodies(ctx, &n_before)) != NB_OK) die(ctx, "nb_num_bodies", rc);
-        if ((rc = nb_step(ctx, 1)) != NB_OK) die(ctx, "nb_step", rc);
-        if (do_images) {
-            // the image rendered after iteration k is written during iteration k + 1 (:513-522)
-            if (pending >= 0 && (it - 1) % every == 0) {
-                const std::string path = std::string(cfg.imagePath) + "/iteration_" + std::to_string(pending) + ".ppm";
-                printf("Saving (%dx%d) to disk\n", cfg.imgWidth, cfg.imgHeight);  // :356
-                fflush(stdout);
-                if (nb_write_pgm(path.c_str(), img.data(), cfg.imgWidth, cfg.imgHeight) != NB_OK) {
-                    fprintf(stderr, "Error writing image to file:%s\nEnsure the the folder exists\n", path.c_str());   // :365-369
-                    return 1;
-                }
-                pending = -1;
-            }
-            if (it % every == 0) {                  // :529-539
-                const int grid = render_all ? 0x7fffffff : 128 * (n_before < 128 ? 1 : n_before / 128);                  // :473,535
-                if ((rc = nb_render_grid(ctx, img.data(), cfg.imgWidth, cfg.imgHeight, grid)) != NB_OK) die(ctx, "nb_render", rc);
-                pending = it;
-            }
-        }
-        if (evf && (it % 64 == 63 || it == total - 1)) {
-            int cnt = 0;
-            if ((rc = nb_events(ctx, evbuf.data(), (int)evbuf.size(), &cnt)) != NB_OK) die(ctx, "nb_events", rc);
-            for (int k = 0; k < cnt; ++k)
-                fprintf(evf, "%d,%d,%d,%d\n", evbuf[k].step, evbuf[k].i, evbuf[k].j, evbuf[k].kind);
-        }
-    }
-    if ((rc = nb_sync(ctx)) != NB_OK) die(ctx, "nb_sync", rc);                    // CUDA_SYNC_CHECK, :546
-    if (evf) fclose(evf);
-    if (!dump_state.empty()) {
-        int n = 0;
-        if ((rc = nb_download(ctx, block.data(), n0, &n)) != NB_OK) die(ctx, "nb_download", rc);
-        FILE *f = fopen(dump_state.c_str(), "wb");
-        if (!f) { fprintf(stderr, "cannot open %s\n", dump_state.c_str()); return 1; }
-        const int32_t n32 = n;
-        fwrite(&n32, sizeof(n32), 1, f);
-        fwrite(block.data(), 24, (size_t)n, f);
-        fclose(f);
-    }
-    nb_destroy(ctx);
     printf("Time taken: %.4f\n", now_s() - start);                                // :548
     return 0;
 }

@@ -2,6 +2,7 @@
 // candidate pairs.  Same compile flags as nbody_kernels.cu (-fmad=false: every fused multiply-add is explicit).
 #include "nbody_device.cuh"
 #include "nbody_ptx.cuh"
+#include "nbody_sym.cuh"
 
 namespace nb {
 namespace {
@@ -92,83 +93,6 @@ struct SymProducer {              // thread 0's walk over the work queue (shared
     int I, J, I1, J0, J1, diag, r0, r1;
 };
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void red_add64(long long *addr, long long v)
-{
-    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
-}
-
-// fixed-point image of a float sum: v * 2^k rounded to the nearest integer (the product is exact)
-__device__ __forceinline__ long long to_fixed(float v, float fscale) { return __float2ll_rn(v * fscale); }
-
-template <bool TEST, int IPT>
-__device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
-                                             const float (&nx)[IPT], const float (&ny)[IPT],
-                                             const float (&nm)[IPT], const float (&thr)[IPT], const float2 s2,
-                                             float2 (&tfx)[IPT], float2 (&tfy)[IPT], unsigned &mask, const int lane)
-{
-    const int src = (lane + 1) & 31;
-#pragma unroll
-    for (int s = 0; s < 32; ++s) {
-        bool flagged = false;
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const float2 dx = __fadd2_rn(xs, make_float2(nx[q], nx[q]));
-            const float2 dy = __fadd2_rn(ys, make_float2(ny[q], ny[q]));
-            const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, s2));
-            const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-            float2 i3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
-            if (TEST) {                           // a pair that passes the pre-test stays out of the sums
-                const bool f0 = d2.x <= thr[q], f1 = d2.y <= thr[q];
-                i3.x = f0 ? 0.f : i3.x;
-                i3.y = f1 ? 0.f : i3.y;
-                flagged |= f0 | f1;
-            }
-            const float2 sj = __fmul2_rn(i3, ms);
-            const float2 si = __fmul2_rn(i3, make_float2(nm[q], nm[q]));
-            tfx[q] = __ffma2_rn(dx, sj, tfx[q]);
-            tfy[q] = __ffma2_rn(dy, sj, tfy[q]);
-            gx = __ffma2_rn(dx, si, gx);
-            gy = __ffma2_rn(dy, si, gy);
-        }
-        if (TEST) mask |= flagged ? (1u << s) : 0u;
-        xs.x = __shfl_sync(0xffffffffu, xs.x, src);
-        xs.y = __shfl_sync(0xffffffffu, xs.y, src);
-        ys.x = __shfl_sync(0xffffffffu, ys.x, src);
-        ys.y = __shfl_sync(0xffffffffu, ys.y, src);
-        ms.x = __shfl_sync(0xffffffffu, ms.x, src);
-        ms.y = __shfl_sync(0xffffffffu, ms.y, src);
-        gx.x = __shfl_sync(0xffffffffu, gx.x, src);
-        gx.y = __shfl_sync(0xffffffffu, gx.y, src);
-        gy.x = __shfl_sync(0xffffffffu, gy.x, src);
-        gy.y = __shfl_sync(0xffffffffu, gy.y, src);
-    }
-}
-
-__device__ __forceinline__ void push_candidate(const DevState &st, const int rank, const int row, const int partner)
-{
-    if (st.xbuf) {                                // sharded: the pair travels to every rank (sym_chain_kernel threads it)
-        const unsigned idx = atomicAdd(&x_header(st, rank)->count, 1u);
-        if (idx < (unsigned)st.x_cap) {
-            x_pairs(st, rank)[idx] = make_int2(row, partner);
-        } else {
-            st.ctr->overflow_flag = 1;
-        }
-        return;
-    }
-    const unsigned idx = atomicAdd(&st.ctr->cand_count, 1u);
-    if (idx < (unsigned)st.cand_cap) {
-        const int prev = atomicExch(&st.head[row], (int)idx);
-        st.cand[idx] = make_int2(partner, prev);
-    } else {
-        st.ctr->overflow_flag = 1;
-    }
-}
-
 // The flagged (lane, sub-step) pairs of one round, re-evaluated with the reference predicate.  The ring is home again:
 // lane p holds j pair p and its accumulators; in sub-step s lane l met j pair (l + s) % 32.  Ig / Jg: the tiles in
 // global memory (radius and original-index planes are not staged); `own`: rows and chunk come from the same tile --
@@ -247,7 +171,7 @@ __global__ void __launch_bounds__(kSymThreads, SymGeom<IPT>::kMinBlocks) force_s
     __shared__ int4 s_desc[kStages];              // per ring stage: {I, J, flags, -}; I < 0: end of work
     __shared__ SymProducer s_prod;
     __shared__ float4 s_rb[kSymThreads / 32];     // per warp: bounding box of its 128 rows (sorted order)
-    if (!st.desc->sym) return;
+    if (st.desc->sym != 1) return;
     float *ring = reinterpret_cast<float *>(sym_dyn);
     float4 *gpriv = reinterpret_cast<float4 *>(sym_dyn + kStages * kSymStageBytes);
     long long *acc_s = reinterpret_cast<long long *>(sym_dyn + kStages * kSymStageBytes + G::kGprivBytes);

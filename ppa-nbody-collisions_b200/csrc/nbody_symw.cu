@@ -1,0 +1,200 @@
+// nbody_symw.cu -- the two-sided force kernel for SMALL n (below the sort threshold, one GPU): one WARP per work item,
+// bodies' own order, no shared memory, no barrier.  Same compile flags as nbody_kernels.cu.
+//
+// The CTA-per-tile-pair kernel of nbody_sym.cu needs tens of tile pairs per CTA to hide what a tile pair costs to set
+// up (row loads, the TMA ring, one barrier phase); at n = 16 384 there are 528 tile pairs for 444 CTAs.  Here the unit
+// of work is what one warp does in one ROUND of that kernel: a group of 128 rows (4 per lane) against chunks of 64
+// bodies (one pair per lane, handed round the lanes together with its accumulators: the same systolic loop,
+// sym_substeps).  Work items are (group g, run of chunks) with chunk index >= 2 g -- the triangle of unordered pairs --
+// taken from a queue by every warp on its own, so the 24 warps of an SM are always in different phases and hide each
+// other's loads.  The two chunks that make up the group itself are evaluated one-sided (every ordered pair of the
+// group is met there on its own; the self pair drops out in the exact path).
+//
+// Everything arrives by plain 16-byte loads from the body store (float4 {x, y, m, r}; the radius rides along for the
+// exact path) and leaves through RED.ADD.64 into the fixed-point force sums (nbody_sym.cuh): 4 per lane and round for
+// the chunk's bodies, 8 per lane and item for the rows.  Every round carries the collision pre-test (there are no
+// bounding boxes on the bodies' own order); pairs that pass it are left out of the packed sums and re-evaluated
+// exactly afterwards, as in the large kernel.
+#include "nbody_sym.cuh"
+
+namespace nb {
+namespace {
+
+constexpr int kWThreads = 128;                 // 4 independent warps per CTA
+constexpr int kWIpt = kWGroup / 32;            // rows per lane
+
+__device__ __forceinline__ bool symw_decode(const WGeom &w, const int id, int &g, int &s)
+{
+    const int pi = id / w.L;
+    int off = id - pi * w.L;
+    const int s0a = (2 * pi) / w.run, na = w.S - s0a;
+    if (off < na) {
+        g = pi;
+        s = s0a + off;
+        return true;
+    }
+    off -= na;
+    const int gb = w.G - 1 - pi;
+    if (gb == pi) return false;
+    const int s0b = (2 * gb) / w.run, nb_ = w.S - s0b;
+    if (off < nb_) {
+        g = gb;
+        s = s0b + off;
+        return true;
+    }
+    return false;
+}
+
+// the flagged (lane, sub-step) pairs of one round, exactly (see sym_redo in nbody_sym.cu; here radii and indices are at hand)
+__device__ __forceinline__ void symw_redo(const DevState &st, const int n, const int rbase, const int cbase, const bool own,
+                                          const float soft2, const unsigned mask, const float2 xs, const float2 ys,
+                                          const float2 ms, const float2 rj, float2 &gx, float2 &gy,
+                                          const float (&nx)[kWIpt], const float (&ny)[kWIpt], const float (&nm)[kWIpt],
+                                          const float (&ri)[kWIpt], const float (&thr)[kWIpt], float2 (&tfx)[kWIpt],
+                                          float2 (&tfy)[kWIpt], const int lane, unsigned &n_redo)
+{
+    unsigned any = __reduce_or_sync(0xffffffffu, mask);
+#pragma unroll 1
+    while (any) {
+        const int s = __ffs(any) - 1;
+        any &= any - 1u;
+        ++n_redo;
+        const int p = (lane + s) & 31;
+        const float xj[2] = {__shfl_sync(0xffffffffu, xs.x, p), __shfl_sync(0xffffffffu, xs.y, p)};
+        const float yj[2] = {__shfl_sync(0xffffffffu, ys.x, p), __shfl_sync(0xffffffffu, ys.y, p)};
+        const float mj[2] = {__shfl_sync(0xffffffffu, ms.x, p), __shfl_sync(0xffffffffu, ms.y, p)};
+        const float rjj[2] = {__shfl_sync(0xffffffffu, rj.x, p), __shfl_sync(0xffffffffu, rj.y, p)};
+        float gxe[2] = {0.f, 0.f}, gye[2] = {0.f, 0.f};
+        if ((mask >> s) & 1u) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int oj = cbase + 2 * p + e;
+#pragma unroll
+                for (int q = 0; q < kWIpt; ++q) {
+                    const int oi = rbase + 32 * q + lane;
+                    const float dx = xj[e] + nx[q], dy = yj[e] + ny[q];
+                    const float d2 = fmaf(dx, dx, dy * dy);
+                    const float d2s = soft2 > 0.f ? fmaf(dx, dx, fmaf(dy, dy, soft2)) : d2;
+                    if (d2s <= thr[q]) {                          // else: the pair was part of the packed sums
+                        const float rsum = ri[q] + rjj[e];
+                        if (oi >= n || oj >= n || oi == oj) {
+                            // padding, or the self pair: nothing
+                        } else if (d2 <= rsum * rsum) {           // src/nbody.cu:126-134
+                            push_candidate(st, 0, oi, oj);
+                            if (!own) push_candidate(st, 0, oj, oi);
+                        } else {
+                            const float inv = rsqrt_approx(d2s);
+                            const float i3 = (inv * inv) * inv;
+                            const float sj = i3 * mj[e], si = i3 * nm[q];
+                            tfx[q].x = fmaf(dx, sj, tfx[q].x);
+                            tfy[q].x = fmaf(dy, sj, tfy[q].x);
+                            gxe[e] = fmaf(dx, si, gxe[e]);
+                            gye[e] = fmaf(dy, si, gye[e]);
+                        }
+                    }
+                }
+            }
+        }
+        const int from = (lane - s) & 31;
+        gx.x += __shfl_sync(0xffffffffu, gxe[0], from);
+        gx.y += __shfl_sync(0xffffffffu, gxe[1], from);
+        gy.x += __shfl_sync(0xffffffffu, gye[0], from);
+        gy.y += __shfl_sync(0xffffffffu, gye[1], from);
+    }
+}
+
+__global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState st, const StepParams p)
+{
+    if (st.desc->sym != 2) return;
+    const int lane = threadIdx.x & 31;
+    const int n = st.desc->n;
+    const float rmax = st.desc->rmax, fscale = st.desc->fscale;
+    const float2 s2 = make_float2(p.soft2, p.soft2);
+    const WGeom w = symw_geom(n, st.desc->sym_S);          // sym_S: chunks per work item on this path (plan)
+    const float4 *__restrict__ pm = st.pm;
+    unsigned n_rounds = 0, n_redo = 0;
+
+    // the next id is fetched while the current item is being worked on
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+#pragma unroll 1
+    for (;;) {
+        const unsigned id = __shfl_sync(0xffffffffu, next, 0);
+        if (id >= (unsigned)w.ids) break;
+        if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+        int g, s;
+        if (!symw_decode(w, (int)id, g, s)) continue;
+        const int rbase = kWGroup * g;
+        float nx[kWIpt], ny[kWIpt], nm[kWIpt], ri[kWIpt], thr[kWIpt];
+        float2 tfx[kWIpt], tfy[kWIpt];
+#pragma unroll
+        for (int q = 0; q < kWIpt; ++q) {
+            const int i = rbase + 32 * q + lane;
+            const bool real = i < n;
+            const float4 b = real ? pm[i] : make_float4(kDummyCoord, kDummyCoord, 0.f, 0.f);
+            nx[q] = -b.x;
+            ny[q] = -b.y;
+            nm[q] = -b.z;
+            ri[q] = b.w;
+            const float rr = b.w + rmax;
+            const float bound = p.soft2 > 0.f ? (rr * rr + p.soft2) * 1.000001f : rr * rr;
+            thr[q] = real ? bound : -1.0f;                 // pads never flag
+            tfx[q] = make_float2(0.f, 0.f);
+            tfy[q] = make_float2(0.f, 0.f);
+        }
+        const int c_lo = max(s * w.run, 2 * g), c_hi = min((s + 1) * w.run, w.C);
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+            const bool own = (c >> 1) == g;
+            const int cbase = kWChunk * c, j0 = cbase + 2 * lane;
+            const float4 pad = make_float4(kPadCoord, kPadCoord, 0.f, 0.f);
+            const float4 b0 = j0 < n ? pm[j0] : pad, b1 = j0 + 1 < n ? pm[j0 + 1] : pad;
+            float2 xs = make_float2(b0.x, b1.x), ys = make_float2(b0.y, b1.y), ms = make_float2(b0.z, b1.z);
+            const float2 rj = make_float2(b0.w, b1.w);
+            float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
+            unsigned mask = 0;
+            sym_substeps<true, kWIpt>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+            if (__any_sync(0xffffffffu, mask != 0u))
+                symw_redo(st, n, rbase, cbase, own, p.soft2, mask, xs, ys, ms, rj, gx, gy, nx, ny, nm, ri, thr, tfx, tfy, lane, n_redo);
+            ++n_rounds;
+            if (!own) {                                    // the chunk's bodies: {gx0, gx1, gy0, gy1} of bodies j0, j0 + 1
+                long long *dst = st.facc + 2 * (size_t)j0;
+                red_add64(dst, to_fixed(gx.x, fscale));
+                red_add64(dst + 1, to_fixed(gy.x, fscale));
+                red_add64(dst + 2, to_fixed(gx.y, fscale));
+                red_add64(dst + 3, to_fixed(gy.y, fscale));
+            }
+        }
+        long long *dst = st.facc + 2 * ((size_t)rbase + lane);
+#pragma unroll
+        for (int q = 0; q < kWIpt; ++q) {
+            red_add64(dst + 64 * q, to_fixed(tfx[q].x + tfx[q].y, fscale));
+            red_add64(dst + 64 * q + 1, to_fixed(tfy[q].x + tfy[q].y, fscale));
+        }
+    }
+    if (p.count_stats && lane == 0) {
+        atomicAdd(&st.ctr->fast_chunks, (unsigned long long)n_rounds * 2ull);
+        atomicAdd(&st.ctr->exact_chunks, (unsigned long long)n_redo);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_force_symw(const DevState &st, const StepParams &p, cudaStream_t s)
+{
+    force_symw_kernel<<<p.symw_grid, kWThreads, 0, s>>>(st, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+int force_symw_occupancy(int *regs)
+{
+    int occ = 0;
+    cudaFuncAttributes fa = {};
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel, kWThreads, 0);
+    cudaFuncGetAttributes(&fa, force_symw_kernel);
+    if (regs) *regs = fa.numRegs;
+    return occ;
+}
+
+}  // namespace nb

@@ -198,3 +198,51 @@ def test_sharded_crossing_sort_threshold_inside_one_call(nb, tmp_path, world):
     mp.spawn(_worker_calls, args=(world, _free_port(), n0, calls, str(tmp_path), sort_min_n, 0, dense), nprocs=world, join=True)
     ns = _check_against_one_gpu(nb, tmp_path, world, n0, calls, sort_min_n, 0, dense)
     assert ns[0] < sort_min_n < n0, f"the scenario must cross the threshold inside the first call (n after it: {ns[0]})"
+
+
+# ---------------------------------------------------------------------------------------------------
+# The C++ host: `nbody --gpus N` (one thread + one context per GPU, NCCL between them) against `nbody --gpus 1`
+# ---------------------------------------------------------------------------------------------------
+def _driver(nb, cwd, *args):
+    import subprocess
+    r = subprocess.run([str(nb.DRIVER_PATH), "--no-images", *args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def _read_state(path):
+    raw = path.read_bytes()
+    n = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
+    return np.frombuffer(raw[4:], dtype=np.float32), n
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cpp_driver_multi_gpu(nb, tmp_path, world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cfg = ("particleCount={n}\ntotalIterations={it}\nsave_Image_Every_Xth_Iteration=100\ntimestep=0.2f\nradiusGrowthRate=0.1f\n"
+           "minRandBodyMass=1e4f\nmaxRandBodyMass=1e17f\nminRadius=50.f\nmaxRadius=200.f\nimgWidth=32\nimgHeight=32\n"
+           "fieldWidth={f}\nfieldHeight={f}\nimagePath=.\n")
+    # all-pairs coverage above the sort threshold: the two-sided kernel's integer force sums make the result independent
+    # of the number of GPUs, bit for bit -- state, stdout and the merged event list
+    (tmp_path / "nbodyConfig.txt").write_text(cfg.format(n=60000, it=5, f=190000))
+    out1 = _driver(nb, tmp_path, "--coverage", "full", "--dump-state", "one.bin", "--dump-events", "one.csv")
+    outw = _driver(nb, tmp_path, "--coverage", "full", "--gpus", str(world), "--dump-state", "many.bin", "--dump-events", "many.csv")
+    strip = lambda o: [ln for ln in o.splitlines() if not ln.startswith("Time taken")]
+    assert strip(out1) == strip(outw)
+    assert (tmp_path / "one.bin").read_bytes() == (tmp_path / "many.bin").read_bytes()
+    assert (tmp_path / "one.csv").read_text() == (tmp_path / "many.csv").read_text()
+    assert len((tmp_path / "one.csv").read_text().splitlines()) > 100
+    # the reference's own coverage (one-sided kernel, rows sharded): same events and survivors, masses and radii bit for
+    # bit, trajectories within the summation-order tolerance
+    (tmp_path / "nbodyConfig.txt").write_text(cfg.format(n=5000, it=6, f=20000))
+    _driver(nb, tmp_path, "--dump-state", "one.bin", "--dump-events", "one.csv")
+    _driver(nb, tmp_path, "--gpus", str(world), "--dump-state", "many.bin", "--dump-events", "many.csv")
+    assert (tmp_path / "one.csv").read_text() == (tmp_path / "many.csv").read_text()
+    a, na = _read_state(tmp_path / "one.bin")
+    b, nbb = _read_state(tmp_path / "many.bin")
+    assert na == nbb and na < 5000
+    pa, va, ma, ra = nb.split(a, na)
+    pb, vb, mb, rb = nb.split(b, nbb)
+    assert np.array_equal(ma.view(np.uint32), mb.view(np.uint32)) and np.array_equal(ra.view(np.uint32), rb.view(np.uint32))
+    assert np.abs(va - vb).max() <= 1e-4 * np.abs(va).max() and np.abs(pa - pb).max() <= 1e-5 * 20000

@@ -26,7 +26,14 @@ POS_TOL = 1e-5
 VEL_TOL = 1e-4
 
 
-def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False, dt=0.2):
+# Free-running bounds with a stated K (tools/free_running_divergence.py on a B200, profiles/r02_free_running_divergence.jsonl:
+# the 16 384-body scenarios -- shipped square in both coverages, disc -- stay within 1e-4 max|v| for every body until step
+# 32..39, within 1e-3 until step 55 or beyond, never reach 1e-2 in 60 steps, and at most 3 bodies are beyond 1e-4):
+# every body within VEL_TOL for K <= 20 steps, within 10 VEL_TOL for K <= 50, within 100 VEL_TOL after that.
+FREE_RUNNING_K = (20, 50)
+
+
+def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False, dt=0.2, step=None):
     assert n_gpu == n_cpu, f"{tag}: n {n_gpu} != {n_cpu}"
     if n_cpu == 0:
         return
@@ -35,15 +42,21 @@ def _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, tag, single_step=False,
     assert np.array_equal(mg.view(np.uint32), mc.view(np.uint32)), f"{tag}: masses not bit-exact"
     assert np.array_equal(rg.view(np.uint32), rc.view(np.uint32)), f"{tag}: radii not bit-exact"
     vmax = max(float(np.abs(vc).max()), 1e-30)
+    if single_step:
+        worst = VEL_TOL
+    elif step is not None:                        # a scenario with a measured divergence schedule
+        worst = VEL_TOL if step < FREE_RUNNING_K[0] else (10 * VEL_TOL if step < FREE_RUNNING_K[1] else 100 * VEL_TOL)
+    else:
+        worst = 100 * VEL_TOL
     # p' = fma(dt, v', p): a position inherits dt times the velocity error (matters only in violent scenarios)
-    pos_tol = POS_TOL * field + (VEL_TOL if single_step else 100 * VEL_TOL) * vmax * dt
+    pos_tol = POS_TOL * field + worst * vmax * dt
     assert np.abs(pg - pc).max() <= pos_tol, f"{tag}: positions off by {np.abs(pg - pc).max()} (tolerance {pos_tol})"
     dv = np.abs(vg - vc)
     # single bodies in a close pass amplify the reference's own summation noise step over step (chaos):
-    # bound the bulk tightly and the worst body loosely
+    # bound the bulk tightly and the worst body by the schedule above
     assert np.quantile(dv, 0.999) <= VEL_TOL * vmax, f"{tag}: 99.9% of velocities off by {np.quantile(dv, 0.999)} of {vmax}"
-    worst = VEL_TOL if single_step else 100 * VEL_TOL
-    assert dv.max() <= worst * vmax, f"{tag}: velocities off by {dv.max()} of {vmax}"
+    assert int((dv.max(axis=1) > VEL_TOL * vmax).sum()) <= max(8, n_cpu // 1000), f"{tag}: too many bodies beyond {VEL_TOL} max|v|"
+    assert dv.max() <= worst * vmax, f"{tag}: velocities off by {dv.max()} of {vmax} (bound {worst})"
 
 
 def _compare_events(ev, ev_cpu, tag):
@@ -54,7 +67,7 @@ def _compare_events(ev, ev_cpu, tag):
 
 
 def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=0.1, trace=None, flags=0, resync=False,
-                      sort_min_n=0, softening=0.0):
+                      sort_min_n=0, softening=0.0, scheduled=False):
     sim = nb.Simulation(n0, dt=dt, growth=growth, field_w=field, field_h=field, coverage=coverage,
                         event_capacity=max(64 * n0, 4096), flags=flags, sort_min_n=sort_min_n, softening=softening)
     try:
@@ -72,7 +85,8 @@ def _run_side_by_side(nb, O, block0, n0, steps, coverage, field, dt=0.2, growth=
             got, n_gpu = sim.download()
             if trace is not None:
                 assert n_gpu == trace[s]["n"], f"step {s}: n differs from the reference kernels' golden trace"
-            _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, f"step {s}", single_step=resync or s == 0, dt=dt)
+            _compare_state(nb, O, got, n_gpu, cpu, n_cpu, field, f"step {s}", single_step=resync or s == 0, dt=dt,
+                           step=s if scheduled else None)
             ev = sim.events()
             assert (ev["step"] == (0 if resync else s)).all()
             _compare_events(ev, ev_cpu, f"step {s}")
@@ -110,7 +124,7 @@ def test_reference_coverage_shipped_60_steps(nb, oracle, gpuref_golden):
     sc = gpuref_golden["scenarios"]["shipped"]
     block0 = nb.generate(nb.SCENARIO_SQUARE, sc["n0"])
     assert np.array_equal(block0, oracle.init_square(sc["n0"]))
-    st = _run_side_by_side(nb, oracle, block0, sc["n0"], 60, nb.COVERAGE_REFERENCE, sc["field"], trace=sc["trace"])
+    st = _run_side_by_side(nb, oracle, block0, sc["n0"], 60, nb.COVERAGE_REFERENCE, sc["field"], trace=sc["trace"], scheduled=True)
     assert st["n"] == 10147
 
 
@@ -133,7 +147,7 @@ def test_full_coverage(nb, oracle, n, field, steps):
 
 def test_full_coverage_shipped_20_steps(nb, oracle):
     block0 = nb.generate(nb.SCENARIO_SQUARE, 16384)
-    _run_side_by_side(nb, oracle, block0, 16384, 20, nb.COVERAGE_FULL, 100000)
+    _run_side_by_side(nb, oracle, block0, 16384, 20, nb.COVERAGE_FULL, 100000, scheduled=True)
 
 
 def test_scalar_force_kernel_and_no_graph(nb, oracle):
@@ -145,7 +159,7 @@ def test_disc_scenario_full(nb, oracle):
     """BASELINE config 2 shape (uniform disc, v = 0), reduced step count."""
     n = 16384
     block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5)
-    _run_side_by_side(nb, oracle, block0, n, 10, nb.COVERAGE_FULL, 100000)
+    _run_side_by_side(nb, oracle, block0, n, 10, nb.COVERAGE_FULL, 100000, scheduled=True)
 
 
 def test_collapsing_cluster_first_steps(nb, oracle):
@@ -225,7 +239,7 @@ def test_cluster_131072_four_steps_against_the_oracle(nb, oracle):
     n, field = 131072, 200000
     block0 = nb.generate(nb.SCENARIO_DISC, n, extent=1e5, field_w=field, field_h=field)
     st = _run_side_by_side(nb, oracle, block0, n, 4, nb.COVERAGE_FULL, field)
-    assert st["pair_halving"] == 1 and st["culled_parts"] > 0 and st["n"] < 80000
+    assert st["pair_halving"] == 1 and st["culled_parts"] > 0 and st["n"] < 90000
 
 
 @pytest.mark.parametrize("config,checkpoints", [("disc1m", (5, 10, 20)), ("cluster", (2, 8, 30))])
@@ -526,11 +540,16 @@ def test_two_sided_force_kernel(nb, oracle, n, field, steps, softening):
     assert st["exact_chunks"] > 0
 
 
-@pytest.mark.parametrize("n,field,steps", [(8000, 20000, 5), (7000, 30000, 4), (16384, 60000, 6), (16384, 100000, 8)])
-def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps):
-    """Below the sort threshold one GPU runs the two-sided kernel on the bodies' own order (every round pre-tested, tile pairs
-    split into quarter work items), down to 6144 bodies; the first two scenarios fall through that bound while running
-    (oracle: 8000 -> 5071 and 7000 -> 5780 after the first step), so two-sided and one-sided steps follow each other."""
+@pytest.mark.parametrize("n,field,steps", [(8000, 20000, 5), (1500, 4000, 4), (2000, 5000, 3), (16384, 60000, 6), (16384, 100000, 8),
+                                           (33000, 140000, 3)])
+@pytest.mark.parametrize("small", [2, 1])
+def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps, small, monkeypatch):
+    """Below the sort threshold one GPU runs a two-sided kernel on the bodies' own order, every round pre-tested: the
+    warp-per-work-item kernel of nbody_symw.cu (small = 2, the default) from 1024 bodies on; the second and third scenario
+    fall through that bound while running (oracle: 1500 -> 324 and 2000 -> 491 after the first step), so two-sided and
+    one-sided steps follow each other.  small = 1 runs the same steps on the CTA-per-tile-pair kernel instead (tile pairs
+    split into quarter work items), which stays selectable for measurements."""
+    monkeypatch.setenv("NBODY_B200_SYM_SMALL", str(small))
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
     sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL)
     sim.upload(block0, n)
@@ -538,7 +557,7 @@ def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps):
     sim.close()
     st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field)
     assert st["culled_parts"] == 0 and st["exact_chunks"] > 0
-    assert st["pair_halving"] == (1 if st["n"] >= 6144 else 0)
+    assert st["pair_halving"] == (1 if st["n"] >= 1024 else 0)
     _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_GRAPH)
     st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_ONE_SIDED)
     assert st["pair_halving"] == 0 and st["sym_regs"] == 0
@@ -618,5 +637,5 @@ def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps, sort_min
         assert (np.abs(p_after - mv.sum(axis=0)) <= 1e-5 * np.abs(mv).sum(axis=0) + 1e-30).all(), f"step {s}: momentum not conserved"
     assert merged_any
     st = sim.stats()
-    assert st["pair_halving"] == (1 if coverage == 1 and (sort_min_n > 0 or st["n"] >= 6144) and st["n"] >= 1024 else 0)
+    assert st["pair_halving"] == (1 if coverage == 1 and st["n"] >= 1024 else 0)
     sim.close()
