@@ -21,14 +21,18 @@ __device__ __forceinline__ void red_add64(long long *addr, long long v)
 // fixed-point image of a float sum: v * 2^k rounded to the nearest integer (the product is exact)
 __device__ __forceinline__ long long to_fixed(float v, float fscale) { return __float2ll_rn(v * fscale); }
 
-template <bool TEST, int IPT>
+// UNROLL: sub-steps per loop iteration.  The CTA-level kernel unrolls all 32 (its 8 warps run in step and share the
+// fetched instructions; the back-edge of a partially unrolled loop costs register moves).  The warp-level kernel must
+// not: its 24 warps per SM are all in different places, and 47 KB of straight-line code per round thrash the
+// instruction cache (ncu: 3 warps stalled on "no instruction" per issue, profiles/r02_force_16k_warp_level_unrolled_ncu.json).
+template <bool TEST, int IPT, int UNROLL = 32>
 __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
                                              const float (&nx)[IPT], const float (&ny)[IPT],
                                              const float (&nm)[IPT], const float (&thr)[IPT], const float2 s2,
                                              float2 (&tfx)[IPT], float2 (&tfy)[IPT], unsigned &mask, const int lane)
 {
     const int src = (lane + 1) & 31;
-#pragma unroll
+#pragma unroll UNROLL
     for (int s = 0; s < 32; ++s) {
         bool flagged = false;
 #pragma unroll

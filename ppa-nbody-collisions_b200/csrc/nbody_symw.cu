@@ -15,6 +15,8 @@
 // the chunk's bodies, 8 per lane and item for the rows.  Every round carries the collision pre-test (there are no
 // bounding boxes on the bodies' own order); pairs that pass it are left out of the packed sums and re-evaluated
 // exactly afterwards, as in the large kernel.
+#include <cstdlib>
+
 #include "nbody_sym.cuh"
 
 namespace nb {
@@ -103,6 +105,7 @@ __device__ __forceinline__ void symw_redo(const DevState &st, const int n, const
     }
 }
 
+template <int UNROLL>
 __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState st, const StepParams p)
 {
     if (st.desc->sym != 2) return;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
             const float2 rj = make_float2(b0.w, b1.w);
             float2 gx = make_float2(0.f, 0.f), gy = make_float2(0.f, 0.f);
             unsigned mask = 0;
-            sym_substeps<true, kWIpt>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
+            sym_substeps<true, kWIpt, UNROLL>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
             if (__any_sync(0xffffffffu, mask != 0u))
                 symw_redo(st, n, rbase, cbase, own, p.soft2, mask, xs, ys, ms, rj, gx, gy, nx, ny, nm, ri, thr, tfx, tfy, lane, n_redo);
             ++n_rounds;
@@ -180,9 +183,26 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
 
 }  // namespace
 
+// sub-steps unrolled per loop iteration: 4 by default (profiles/r02_small_n_sweep.md); NBODY_B200_SYMW_UNROLL for measurements
+static int symw_unroll()
+{
+    static int u = 0;
+    if (u == 0) {
+        const char *e = getenv("NBODY_B200_SYMW_UNROLL");
+        const int v = e ? atoi(e) : 4;
+        u = (v == 2 || v == 8 || v == 32) ? v : 4;
+    }
+    return u;
+}
+
 cudaError_t launch_force_symw(const DevState &st, const StepParams &p, cudaStream_t s)
 {
-    force_symw_kernel<<<p.symw_grid, kWThreads, 0, s>>>(st, p);
+    switch (symw_unroll()) {
+    case 2: force_symw_kernel<2><<<p.symw_grid, kWThreads, 0, s>>>(st, p); break;
+    case 8: force_symw_kernel<8><<<p.symw_grid, kWThreads, 0, s>>>(st, p); break;
+    case 32: force_symw_kernel<32><<<p.symw_grid, kWThreads, 0, s>>>(st, p); break;
+    default: force_symw_kernel<4><<<p.symw_grid, kWThreads, 0, s>>>(st, p); break;
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -191,8 +211,12 @@ int force_symw_occupancy(int *regs)
 {
     int occ = 0;
     cudaFuncAttributes fa = {};
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel, kWThreads, 0);
-    cudaFuncGetAttributes(&fa, force_symw_kernel);
+    switch (symw_unroll()) {
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel<2>, kWThreads, 0); cudaFuncGetAttributes(&fa, force_symw_kernel<2>); break;
+    case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel<8>, kWThreads, 0); cudaFuncGetAttributes(&fa, force_symw_kernel<8>); break;
+    case 32: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel<32>, kWThreads, 0); cudaFuncGetAttributes(&fa, force_symw_kernel<32>); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, force_symw_kernel<4>, kWThreads, 0); cudaFuncGetAttributes(&fa, force_symw_kernel<4>); break;
+    }
     if (regs) *regs = fa.numRegs;
     return occ;
 }
