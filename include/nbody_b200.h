@@ -98,7 +98,7 @@ typedef struct nb_params {
                                  shuffles per evaluation).  Same results as the default (4 rows, 3 CTAs); measured 3 %
                                  slower at n = 262 144 (profiles/r01_two_sided_rows8.log) although the bare loop is 7 %
                                  faster: kept for tuning, never selected by default                                  */
-#define NB_SORT_MIN_N_DEFAULT 40960
+#define NB_SORT_MIN_N_DEFAULT 12288
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
 #define NB_FLAG_VARIANT(v) ((v) << NB_FLAG_VARIANT_SHIFT)

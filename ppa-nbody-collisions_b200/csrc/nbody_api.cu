@@ -34,9 +34,11 @@ struct nb_ctx {
     int variant;
     int force_threads;
     cudaStream_t stream;
-    cudaGraphExec_t graph[2];          // [0] plain step, [1] step + rebuild of the cell-sorted shadow order
-    bool graph_ready[2];
+    cudaGraphExec_t graph[3];          // [0] plain step, [1] step + the cell-sorted order carried over, [2] step + full re-sort
+    bool graph_ready[3];
     StepParams sp_plain;               // sp with the sorted order switched off (what graph[0] bakes in)
+    StepParams sp_resort;              // sp with a full radix sort at the end of the step (graph[2]); sp itself carries the order over
+    unsigned long long host_step;      // steps enqueued since nb_upload: decides carry / re-sort, the same on every rank
     volatile int *host_n;              // pinned + mapped: live body count, written by the device every step
     cudaEvent_t ring[16];              // bounds how far the host runs ahead when it picks a graph per step
     unsigned long long ring_pos;
@@ -48,7 +50,7 @@ struct nb_ctx {
     unsigned char *dev_img;
     size_t dev_img_bytes;
     long long launches;                // kernels of this library executed on behalf of this context (direct + graph nodes)
-    long long graph_nodes[2];          // kernel nodes of graph[k]
+    long long graph_nodes[3];          // kernel nodes of graph[k]
     char err[512];
 };
 
@@ -133,7 +135,7 @@ static void free_all(nb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         if (c->graph_ready[k]) cudaGraphExecDestroy(c->graph[k]);
     for (cudaEvent_t e : c->ring)
         if (e) cudaEventDestroy(e);
@@ -143,7 +145,7 @@ static void free_all(nb_ctx *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
-    void *ptrs[] = {c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
+    void *ptrs[] = {c->st.remap, c->st.carry_count, c->st.mhead, c->st.mnext, c->st.sinv, c->st.jts, c->st.skey[0], c->st.skey[1], c->st.sidx[0], c->st.sidx[1], c->st.shist,
                     c->st.pm,   c->st.vel, c->st.jt,         c->st.post, c->st.fpart, c->st.facc, c->st.xbuf, c->st.head, c->st.cand,
                     c->st.ev,   c->st.tile_count, c->st.desc, c->st.res,  c->st.ctr,   c->dev_block, c->dev_img};
     for (void *p : ptrs)
@@ -290,6 +292,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
         }
         NB_ALLOC(st.shist, sizeof(unsigned) * sort_hist_entries(st.cap));
         NB_ALLOC(st.sinv, sizeof(int) * (size_t)st.cap);
+        NB_ALLOC(st.remap, sizeof(int) * (size_t)st.cap);
+        NB_ALLOC(st.carry_count, sizeof(int) * ((size_t)st.cap / 1024 + 1));
     }
     if (sp.sym) {
         st.slots = tiles * kTJ;
@@ -316,6 +320,9 @@ int nb_create(nb_ctx **out, const nb_params *params)
     NB_ALLOC(st.ctr, sizeof(Counters));
     NB_ALLOC(c->dev_block, (size_t)24 * (st.cap + 4 * world));      // room for the padded arrays of a sharded upload
 #undef NB_ALLOC
+    sp.resort = 0;
+    c->sp_resort = sp;
+    c->sp_resort.resort = 1;
     c->sp_plain = sp;
     c->sp_plain.sort_min_n = 0;
     if (world > 1) c->sp_plain.sym = 0;            // sharded: the two-sided kernel runs on the sorted order only
@@ -390,7 +397,8 @@ int nb_upload(nb_ctx *c, const void *bodies, int n)
     if (c->st.facc) NB_CUDA(c, cudaMemsetAsync(c->st.facc, 0, sizeof(long long) * 2 * c->st.slots, c->stream));
     NB_CUDA(c, launch_ingest(c->st, d_pos, d_vel, d_mass, d_rad, n, c->stream));
     NB_CUDA(c, launch_plan(c->st, c->sp, n, c->stream));
-    if (c->sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, c->sp, c->stream));
+    if (c->sp.sort_min_n > 0) NB_CUDA(c, launch_sort(c->st, c->sp_resort, c->stream));
+    c->host_step = 0;
     // the caller may reuse `bodies` as soon as we return
     NB_CUDA(c, cudaStreamSynchronize(c->stream));
     return NB_OK;
@@ -486,13 +494,15 @@ static int enqueue_step(nb_ctx *c, const StepParams &sp, cudaEvent_t f0, cudaEve
     return NB_OK;
 }
 
+static const StepParams &graph_params(const nb_ctx *c, int which);
+
 static int ensure_graph(nb_ctx *c, int which)
 {
     if (c->graph_ready[which]) return NB_OK;
     cudaGraph_t g = nullptr;
     NB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     const long long c0 = launch_counter();
-    int rc = enqueue_step(c, which ? c->sp : c->sp_plain, nullptr, nullptr);
+    int rc = enqueue_step(c, graph_params(c, which), nullptr, nullptr);
     c->graph_nodes[which] = launch_counter() - c0;      // recorded, not executed: they count once per replay
     launch_counter() = c0;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -508,40 +518,54 @@ static int ensure_graph(nb_ctx *c, int which)
     return NB_OK;
 }
 
-// n_steps steps through the CUDA graphs (or plain launches with NB_FLAG_NO_GRAPH).  A sort-capable context
-// picks, per step, the graph that also rebuilds the sorted order while the live body count (mirrored to pinned
-// host memory by the device) is at or above the threshold, and the lean graph once it has fallen below.  n
-// only shrinks, so a stale (too large) count can only pick the richer graph, whose extra kernels then exit at
-// once; either graph is correct after either.  To keep the count reasonably fresh the host stays at most 16
-// steps ahead of the device.
+// The step parameters of graph `which`: 0 plain, 1 sorted order carried over at the end of the step, 2 full re-sort.
+static const StepParams &graph_params(const nb_ctx *c, int which)
+{
+    return which == 2 ? c->sp_resort : (which ? c->sp : c->sp_plain);
+}
+
+// Which graph the next step uses.  Sorted or plain: by the live body count the device mirrors to pinned host memory (n
+// only shrinks, so a stale -- too large -- count can only pick the richer graph, whose extra kernels then exit at once).
+// Carry or re-sort: by the host's own step counter (every kResortEvery-th step ends with a full radix sort), which is
+// the same on every rank.
+static int pick_graph(nb_ctx *c, bool sorted_graph)
+{
+    if (!sorted_graph) return 0;
+    return (c->host_step + 1) % kResortEvery == 0 ? 2 : 1;
+}
+
+// n_steps steps through the CUDA graphs (or plain launches with NB_FLAG_NO_GRAPH).  To keep the body count reasonably
+// fresh a single-GPU host stays at most 16 steps ahead of its device.
 static int run_steps(nb_ctx *c, int n_steps)
 {
     int rc;
     LaunchScope scope(c);
     const bool sortable = c->sp.sort_min_n > 0;
-    const int entry_which = (sortable && *c->host_n >= c->sp.sort_min_n) ? 1 : 0;
+    const bool entry_sorted = sortable && *c->host_n >= c->sp.sort_min_n;
     for (int s = 0; s < n_steps; ++s) {
-        int which = 0;
+        bool sorted_graph = false;
         if (sortable && c->sp.world > 1) {
-            // sharded: the two graphs hold different collectives (graph[1] also exchanges the two-sided kernel's sums and
+            // sharded: the graphs hold different collectives (the sorted ones also exchange the two-sided kernel's sums and
             // candidates), so the choice must be the same on every rank and cannot depend on how far each host has read
             // ahead of its device.  It is made once per call from the body count at its start -- every sharded nb_step
             // and nb_upload ends with a stream synchronisation, and the replicas hold the same bodies, so every rank
             // reads the same number.  Should the count cross the threshold inside the call, the rich graph's sort and
             // two-sided kernels exit at once (the step descriptor, identical on every rank, does not name them).
-            which = entry_which;
+            sorted_graph = entry_sorted;
         } else if (sortable) {
             cudaEvent_t &slot = c->ring[c->ring_pos % 16];
             if (c->ring_pos >= 16) NB_CUDA(c, cudaEventSynchronize(slot));
-            which = *c->host_n >= c->sp.sort_min_n ? 1 : 0;
+            sorted_graph = *c->host_n >= c->sp.sort_min_n;
         }
+        const int which = pick_graph(c, sorted_graph);
         if (c->par.flags & NB_FLAG_NO_GRAPH) {
-            if ((rc = enqueue_step(c, which ? c->sp : c->sp_plain, nullptr, nullptr)) != NB_OK) return rc;
+            if ((rc = enqueue_step(c, graph_params(c, which), nullptr, nullptr)) != NB_OK) return rc;
         } else {
             if ((rc = ensure_graph(c, which)) != NB_OK) return rc;
             NB_CUDA(c, cudaGraphLaunch(c->graph[which], c->stream));
             c->launches += c->graph_nodes[which];
         }
+        ++c->host_step;
         if (sortable && c->sp.world <= 1) {
             NB_CUDA(c, cudaEventRecord(c->ring[c->ring_pos % 16], c->stream));
             ++c->ring_pos;
@@ -591,8 +615,10 @@ int nb_step_timed(nb_ctx *c, int n_steps, float *ms_total, float *ms_force)
     }
     NB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     LaunchScope scope(c);
-    for (int s = 0; s < n_steps; ++s)
-        if ((rc = enqueue_step(c, c->sp, c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
+    for (int s = 0; s < n_steps; ++s) {
+        if ((rc = enqueue_step(c, graph_params(c, pick_graph(c, c->sp.sort_min_n > 0)), c->fev[2 * s], c->fev[2 * s + 1])) != NB_OK) return rc;
+        ++c->host_step;
+    }
     NB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     NB_CUDA(c, cudaEventSynchronize(c->ev1));
     if (ms_total) NB_CUDA(c, cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
@@ -619,7 +645,8 @@ int nb_step_profile(nb_ctx *c, int n_steps, float ms[5])
     for (int k = 0; k < 5; ++k) ms[k] = 0.f;
     LaunchScope scope(c);
     for (int s = 0; s < n_steps; ++s) {
-        if ((rc = enqueue_step(c, c->sp, nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
+        if ((rc = enqueue_step(c, graph_params(c, pick_graph(c, c->sp.sort_min_n > 0)), nullptr, nullptr, c->fev.data())) != NB_OK) return rc;
+        ++c->host_step;
         NB_CUDA(c, cudaEventSynchronize(c->fev[5]));
         for (int k = 0; k < 5; ++k) {
             float t = 0.f;

@@ -39,8 +39,12 @@ constexpr int kSC = 32;                      // j bodies per sub-chunk (granular
 constexpr int kStages = 4;                   // TMA ring depth
 constexpr int kCompactThreads = 256;
 constexpr int kCompactTile = 1024;           // rows per compaction tile (4 rounds of 256)
+constexpr int kResortEvery = 32;             // the cell-sorted order is rebuilt from scratch every so many steps and carried
+                                             // over (survivors keep their places) in between: bodies move little per step
 constexpr int kSymSMax = 8;                  // two-sided force kernel: a block of the pair triangle is S x S tile pairs, S <= 8
-constexpr int kSymMinNDefault = 1024;        // smallest n the two-sided kernel takes on the bodies' own order (one GPU)
+constexpr int kSymMinNDefault = 12288;       // smallest n the warp-level two-sided kernel takes (one GPU); below it the one-sided
+                                             // kernel is faster (profiles/r02_small_n_sweep.md)
+constexpr int kSymWarpMaxN = 40960;          // from here on the CTA-level kernel of nbody_sym.cu takes over
 constexpr int kWGroup = 128;                 // warp-level two-sided kernel (nbody_symw.cu): rows per group, bodies per chunk
 constexpr int kWChunk = 64;
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0
@@ -48,6 +52,7 @@ constexpr float kDummyCoord = -1.0e18f;      // inactive i lanes sit here
 
 struct StepDesc {                 // rewritten on the device at the end of every step (plan)
     int n;                        // live bodies
+    int n_prev;                   // live bodies of the step before (slots of the order being carried over)
     int blocks;                   // B: j tiles of the reference's visit order        (src/nbody.cu:473)
     int limit_last;               // slots of tile B-1                                (src/nbody.cu:194)
     int limit_first;              // slots of tile 0 (128 unless B == 1)
@@ -113,6 +118,7 @@ struct StepParams {
     int count_stats;              // 1: the force kernel counts fast/exact sub-chunks
     int iblock;                   // rows per i-block of the force-kernel variant in use (512 or 1024)
     int merge;                    // 0: the reference's absorb rule; 1: conserving lowest-index merge (opt-in)
+    int resort;                   // this graph's end-of-step order rebuild: 1 full radix sort, 0 carry the previous order over
     int lg_parts_override;        // >= 0: fixed unit size (tuning experiments); -1: cost model
     int sort_min_n;               // > 0: full-coverage steps with n >= sort_min_n use the cell-sorted j stream
     int sym;                      // 1: steps on the cell-sorted order evaluate each unordered pair once (two-sided kernel)
@@ -131,6 +137,8 @@ struct DevState {
     unsigned *skey[2];            // radix sort ping-pong: Morton cell keys
     int *sidx[2];                 //                       body indices (sidx[0][slot] = body after the sort)
     int *sinv;                    // body -> slot
+    int *remap;                   // compaction: body index before -> after (-1: removed); carries the sorted order over
+    int *carry_count;             // survivors per 1024 slots of the previous order
     int *host_n;                  // device pointer to a pinned host int: the live body count after every step
     unsigned *shist;              // 256 x radix blocks
     unsigned char *post;          // world chunks of shard_cap * 24 B

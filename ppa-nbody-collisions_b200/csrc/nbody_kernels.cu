@@ -73,10 +73,12 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     d.finv = 1.0;
     // Two-sided kernel: always on the cell-sorted order; on the bodies' own order (every round pre-tested) from sym_min_n
     // bodies on, one GPU only.  It needs a fixed-point scale for its force sums; without one the one-sided kernel runs.
-    const bool small = !d.sorted && p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n;
+    // Two-sided kernels (all-pairs coverage, a fixed-point scale for the force sums must exist; else the one-sided kernel
+    // runs).  One GPU, sym_min_n <= n < kSymWarpMaxN: a warp per work item (nbody_symw.cu), on the sorted order if the step
+    // has one.  Otherwise, on the sorted order: a CTA per tile pair (nbody_sym.cu).
+    const bool small = p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n && n < kSymWarpMaxN;
     if (p.sym && p.coverage == NB_COVERAGE_FULL && small && p.sym_small == 2 &&
         sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
-        // below the sort threshold: a warp per work item (nbody_symw.cu)
         d.sym = 2;
         d.sym_S = symw_run(n, 4 * (p.symw_grid > 0 ? p.symw_grid : 1));
         d.sym_items = symw_geom(n, d.sym_S).ids;
@@ -106,6 +108,7 @@ __global__ void plan_kernel(DevState st, StepParams p, int n)
     StepDesc d;
     plan_fill(d, p, n, __uint_as_float(st.res->rmax_bits), 0u, __uint_as_float(st.res->mmax_bits),
               __uint_as_float(0x7f800000u - st.res->rmin_inv));
+    d.n_prev = n;
     *st.desc = d;
     st.res->rmax_bits = 0u;
     st.res->mmax_bits = 0u;
@@ -885,8 +888,10 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
                 before += k < warp ? cnt : 0;
                 total += cnt;
             }
+            const int dst_index = run + before + __popc(m & ((1u << lane) - 1u));
+            if (st.remap && i < n) st.remap[i] = keep ? dst_index : -1;
             if (keep) {
-                store_body(st, run + before + __popc(m & ((1u << lane) - 1u)), b, v);
+                store_body(st, dst_index, b, v);
                 rmx = fmaxf(rmx, b.w);
                 mmx = fmaxf(mmx, b.z);
                 rmn = fminf(rmn, b.w);
@@ -928,6 +933,7 @@ __global__ void __launch_bounds__(kCompactThreads) scatter_kernel(const DevState
         StepDesc d;
         plan_fill(d, p, n_new, __uint_as_float(__ldcg(&st.res->rmax_bits)), old.step + 1,
                   __uint_as_float(__ldcg(&st.res->mmax_bits)), __uint_as_float(0x7f800000u - __ldcg(&st.res->rmin_inv)));
+        d.n_prev = old.n;
         *st.desc = d;
         st.res->rmax_bits = 0u;
         st.res->mmax_bits = 0u;
@@ -1163,6 +1169,7 @@ size_t fpart_slabs(int force_grid, int shard_cap, int iblock)
 void plan_host(StepDesc *d, const StepParams *p, int n)
 {
     plan_fill(*d, *p, n, 0.f, 0u, 1.0f, 1.0f);     // unit mass and radius: the fixed-point scale always exists
+    d->n_prev = n;
 }
 
 }  // namespace nb

@@ -160,8 +160,81 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const DevSt
     }
 }
 
-// sorted j-tiles + bounding boxes; slot s of the sorted order holds body sidx[0][s].  One block per tile.
-__global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
+// ------------------------------------------------------------------------------------------------
+// Carrying the order over a compaction (all steps but every kResortEvery-th): bodies move a small fraction of a cell per
+// step, so the previous step's order is as good as a fresh sort for culling (bounding boxes are rebuilt from the current
+// positions either way; correctness never depends on the order).  The survivors keep their relative places: a stable
+// compaction of the slot list through the body compaction's index map -- 2 small kernels instead of the 7 of a sort.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCarryTile = 1024;
+
+__global__ void __launch_bounds__(256) carry_count_kernel(const DevState st)
+{
+    __shared__ int s_cnt[8];
+    if (!st.desc->sorted) return;
+    const int n_prev = st.desc->n_prev;
+    const int base = blockIdx.x * kCarryTile;
+    if (base >= n_prev) return;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < kCarryTile / 256; ++r) {
+        const int s = base + r * 256 + threadIdx.x;
+        if (s < n_prev) cnt += st.remap[st.sidx[0][s]] >= 0 ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += s_cnt[k];
+        st.carry_count[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) carry_scatter_kernel(const DevState st)
+{
+    __shared__ int s_buf[8];
+    __shared__ int s_warp[8];
+    if (!st.desc->sorted) return;
+    const int n_prev = st.desc->n_prev;
+    const int base = blockIdx.x * kCarryTile;
+    if (base >= n_prev) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 256) part += st.carry_count[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_buf[warp] = part;
+    __syncthreads();
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) run += s_buf[k];
+#pragma unroll 1
+    for (int r = 0; r < kCarryTile / 256; ++r) {
+        const int s = base + r * 256 + threadIdx.x;
+        const int now = s < n_prev ? st.remap[st.sidx[0][s]] : -1;
+        const bool keep = now >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = s_warp[k];
+            before += k < warp ? c : 0;
+            total += c;
+        }
+        if (keep) st.sidx[1][run + before + __popc(m & ((1u << lane) - 1u))] = now;
+        run += total;
+    }
+}
+
+// sorted j-tiles + bounding boxes; slot s of the order holds body src[s] (src = the radix sort's result sidx[0], or the
+// carried-over list sidx[1], which is copied into sidx[0] on the way).  One block per tile.
+__global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st, const int resort)
 {
     __shared__ float4 s_box[kTJ / 32];
     if (!st.desc->sorted) return;
@@ -172,7 +245,8 @@ __global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
     float4 b = make_float4(kPadCoord, kPadCoord, 0.f, 0.f);
     int orig = -1;
     if (s < n) {
-        orig = st.sidx[0][s];
+        orig = st.sidx[resort ? 0 : 1][s];
+        if (!resort) st.sidx[0][s] = orig;
         b = st.pm[orig];
         st.sinv[orig] = s;
     }
@@ -215,19 +289,27 @@ __global__ void __launch_bounds__(kTJ) gather_kernel(const DevState st)
 
 cudaError_t launch_sort(const DevState &st, const StepParams &p, cudaStream_t s)
 {
-    const int per_block = sort_per_block(st.cap);
-    const int nblocks = (st.cap + per_block - 1) / per_block;
-    keys_kernel<<<(st.cap + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s>>>(st, p);
-    count_launch();
-    for (int pass = 0; pass < 2; ++pass) {
-        radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+    if (p.resort) {
+        const int per_block = sort_per_block(st.cap);
+        const int nblocks = (st.cap + per_block - 1) / per_block;
+        keys_kernel<<<(st.cap + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s>>>(st, p);
         count_launch();
-        radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
+        for (int pass = 0; pass < 2; ++pass) {
+            radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+            count_launch();
+            radix_scan_kernel<<<1, 1024, 0, s>>>(st, nblocks);
+            count_launch();
+            radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+            count_launch();
+        }
+    } else {
+        const int tiles = (st.cap + kCarryTile - 1) / kCarryTile;
+        carry_count_kernel<<<tiles, 256, 0, s>>>(st);
         count_launch();
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(st, pass, 8 * pass, per_block);
+        carry_scatter_kernel<<<tiles, 256, 0, s>>>(st);
         count_launch();
     }
-    gather_kernel<<<(st.cap + kTJ - 1) / kTJ, kTJ, 0, s>>>(st);
+    gather_kernel<<<(st.cap + kTJ - 1) / kTJ, kTJ, 0, s>>>(st, p.resort);
     count_launch();
     return cudaGetLastError();
 }

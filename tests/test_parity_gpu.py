@@ -540,27 +540,46 @@ def test_two_sided_force_kernel(nb, oracle, n, field, steps, softening):
     assert st["exact_chunks"] > 0
 
 
-@pytest.mark.parametrize("n,field,steps", [(8000, 20000, 5), (1500, 4000, 4), (2000, 5000, 3), (16384, 60000, 6), (16384, 100000, 8),
-                                           (33000, 140000, 3)])
+@pytest.mark.parametrize("n,field,steps", [(8000, 20000, 5), (1500, 4000, 4), (2000, 5000, 3), (16384, 60000, 6), (33000, 140000, 3)])
 @pytest.mark.parametrize("small", [2, 1])
 def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps, small, monkeypatch):
-    """Below the sort threshold one GPU runs a two-sided kernel on the bodies' own order, every round pre-tested: the
-    warp-per-work-item kernel of nbody_symw.cu (small = 2, the default) from 1024 bodies on; the second and third scenario
-    fall through that bound while running (oracle: 1500 -> 324 and 2000 -> 491 after the first step), so two-sided and
-    one-sided steps follow each other.  small = 1 runs the same steps on the CTA-per-tile-pair kernel instead (tile pairs
-    split into quarter work items), which stays selectable for measurements."""
+    """The two-sided kernels WITHOUT the sorted order (NB_FLAG_NO_SORT; every round carries the collision pre-test), with the
+    size bound of the warp-level kernel forced down to 1024 bodies: small = 2 the warp-per-work-item kernel of
+    nbody_symw.cu, small = 1 the CTA-per-tile-pair kernel (tile pairs split into quarter work items), which stays
+    selectable for measurements.  The second and third scenario fall through the bound while running (oracle: 1500 -> 324
+    and 2000 -> 491 after the first step), so two-sided and one-sided steps follow each other."""
     monkeypatch.setenv("NBODY_B200_SYM_SMALL", str(small))
+    monkeypatch.setenv("NBODY_B200_SYM_MIN_N", "1024")
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
-    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL, flags=nb.FLAG_NO_SORT)
     sim.upload(block0, n)
     assert sim.stats()["pair_halving"] == 1 and sim.stats()["sym_regs"] > 0
     sim.close()
-    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field)
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_SORT)
     assert st["culled_parts"] == 0 and st["exact_chunks"] > 0
     assert st["pair_halving"] == (1 if st["n"] >= 1024 else 0)
-    _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_GRAPH)
+    _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_GRAPH | nb.FLAG_NO_SORT)
+
+
+@pytest.mark.parametrize("n,field,steps,scheduled", [(16384, 100000, 40, True), (16384, 45000, 8, False), (20000, 30000, 4, False),
+                                                     (33000, 140000, 3, False), (40000, 160000, 3, False)])
+def test_warp_level_kernel_on_the_sorted_order(nb, oracle, n, field, steps, scheduled):
+    """The default path from 12288 to 40960 bodies on one GPU: the cell-sorted order (re-sorted every 32 steps, carried
+    over the compaction in between) with the warp-per-work-item two-sided kernel, bounding boxes culling the pre-test.
+    The first scenario runs 40 steps (across a re-sort), the second and third fall below 12288 bodies while running
+    (oracle: 16384 -> ... 12402, 12136 after steps 5, 6; 20000 -> 12020 after the first step): sorted two-sided steps
+    are followed by one-sided steps on the bodies' own order."""
+    block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
+    sim = nb.Simulation(n, field_w=field, field_h=field, coverage=nb.COVERAGE_FULL)
+    sim.upload(block0, n)
+    assert sim.stats()["pair_halving"] == 1
+    sim.close()
+    st = _run_side_by_side(nb, oracle, block0, n, steps, nb.COVERAGE_FULL, field, scheduled=scheduled)
+    assert st["culled_parts"] > 0 and st["exact_chunks"] > 0
+    assert st["pair_halving"] == (1 if st["n"] >= 12288 else 0)
+    _run_side_by_side(nb, oracle, block0, n, 3, nb.COVERAGE_FULL, field, flags=nb.FLAG_NO_GRAPH)
     st = _run_side_by_side(nb, oracle, block0, n, 2, nb.COVERAGE_FULL, field, flags=nb.FLAG_ONE_SIDED)
-    assert st["pair_halving"] == 0 and st["sym_regs"] == 0
+    assert st["pair_halving"] == 0 and st["sym_regs"] == 0 and st["culled_parts"] > 0
 
 
 def test_two_sided_is_deterministic_and_agrees_with_one_sided(nb):
@@ -637,5 +656,5 @@ def test_opt_in_conserving_merge(nb, oracle, n, field, coverage, steps, sort_min
         assert (np.abs(p_after - mv.sum(axis=0)) <= 1e-5 * np.abs(mv).sum(axis=0) + 1e-30).all(), f"step {s}: momentum not conserved"
     assert merged_any
     st = sim.stats()
-    assert st["pair_halving"] == (1 if coverage == 1 and st["n"] >= 1024 else 0)
+    assert st["pair_halving"] == (1 if coverage == 1 and ((sort_min_n > 0 and st["n"] >= 1024) or st["n"] >= 12288) else 0)
     sim.close()

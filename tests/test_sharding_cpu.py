@@ -105,15 +105,15 @@ def test_plan_shards_cover_all_rows(nb):
 def test_two_sided_plan_covers_every_tile_pair_once(nb):
     """Host logic of the two-sided force kernel: which steps use it, the cut of the pair triangle into blocks, and the
     deal of the blocks to the ranks -- every unordered tile pair belongs to exactly one block of exactly one rank."""
-    for n, world in ((1023, 1), (1024, 1), (6144, 1), (16384, 1), (40959, 1), (40959, 2), (40960, 1), (49152, 1), (131072, 1),
+    for n, world in ((1023, 1), (12287, 1), (12288, 1), (16384, 1), (16384, 2), (40959, 1), (40959, 2), (40960, 1), (49152, 1), (131072, 1),
                      (1048576, 1), (4194304, 1), (1000003, 2), (1048576, 8), (4194304, 8), (70000, 3)):
         plans = [nb.plan(n, coverage=nb.COVERAGE_FULL, rank=r, world=world) for r in range(world)]
         p = plans[0]
-        is_sorted = n >= 40960
-        # on the cell-sorted order always; on one GPU also on the bodies' own order (warp-level kernel) from 1024 bodies on
-        uses = is_sorted or (world == 1 and n >= 1024)
-        assert p["sorted"] == int(is_sorted) and p["two_sided"] == int(uses), (n, world, p)
-        if not is_sorted:
+        # the cell-sorted order and a two-sided kernel from 12288 bodies on: on one GPU below 40960 bodies the warp-level
+        # kernel, else the CTA-level kernel whose cut of the pair triangle is checked here
+        uses = n >= 12288
+        assert p["sorted"] == int(uses) and p["two_sided"] == int(uses), (n, world, p)
+        if not uses or (world == 1 and n < 40960):
             continue
         T, S, Q = p["n_jtiles"], p["sym_S"], p["sym_Q"]
         # the cut depends on the tile count alone (never on the number of GPUs): one GPU and several round alike
@@ -146,15 +146,16 @@ def test_two_sided_plan_covers_every_tile_pair_once(nb):
 
 def test_two_sided_plan_flags(nb):
     assert nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["two_sided"] == 0 and nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["sorted"] == 1
-    # without the sorted order one GPU still runs it (every round pre-tested), several GPUs do not
-    assert nb.plan(131072, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(131072, flags=nb.FLAG_NO_SORT)["two_sided"] == 1
-    assert nb.plan(131072, flags=nb.FLAG_NO_SORT, world=2)["two_sided"] == 0
+    # without the sorted order one GPU still runs the warp-level kernel below 40960 bodies (every round pre-tested)
+    assert nb.plan(131072, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(131072, flags=nb.FLAG_NO_SORT)["two_sided"] == 0
+    assert nb.plan(30000, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(30000, flags=nb.FLAG_NO_SORT)["two_sided"] == 1
+    assert nb.plan(30000, flags=nb.FLAG_NO_SORT, world=2)["two_sided"] == 0
     assert nb.plan(131072, coverage=nb.COVERAGE_REFERENCE)["two_sided"] == 0
     assert nb.plan(5000, sort_min_n=1024)["two_sided"] == 1 and nb.plan(1023, sort_min_n=1)["two_sided"] == 0
     assert nb.plan(5000, sort_min_n=1024)["sorted"] == 1 and nb.plan(5000, sort_min_n=1024, world=2)["two_sided"] == 1
     p = nb.plan(30000, n_max=131072)                                  # a big context whose body count has dropped
-    assert p["sorted"] == 0 and p["two_sided"] == 1
-    assert nb.plan(30000, n_max=131072, world=2)["two_sided"] == 0 and nb.plan(900, n_max=131072)["two_sided"] == 0
+    assert p["sorted"] == 1 and p["two_sided"] == 1
+    assert nb.plan(30000, n_max=131072, world=2)["two_sided"] == 1 and nb.plan(9000, n_max=131072)["two_sided"] == 0
     assert nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["sorted"] == 1 and nb.plan(131072, flags=nb.FLAG_MERGE_CONSERVING)["two_sided"] == 1
     with pytest.raises(nb.NbodyError):
         nb.plan_block(4, 10)
