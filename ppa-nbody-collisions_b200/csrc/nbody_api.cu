@@ -258,8 +258,11 @@ int nb_create(nb_ctx **out, const nb_params *params)
             if (world == 1) {
                 sp.sym_min_n = kSymMinNDefault;
                 sp.sym_small = 2;
+                sp.symw_queue = 1;
                 if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);       // tuning only
                 if (const char *e = getenv("NBODY_B200_SYM_SMALL")) sp.sym_small = atoi(e) == 1 ? 1 : 2;
+                if (const char *e = getenv("NBODY_B200_SYMW_QUEUE")) sp.symw_queue = atoi(e) != 0;
+                if (const char *e = getenv("NBODY_B200_SYMW_RUN")) sp.symw_run = atoi(e) > 0 ? atoi(e) : 0;
                 int wregs = 0;
                 sp.symw_grid = c->sm_count * std::max(1, force_symw_occupancy(&wregs));
             }

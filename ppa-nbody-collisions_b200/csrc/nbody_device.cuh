@@ -126,6 +126,8 @@ struct StepParams {
     int sym_min_n;                //    smallest n that runs it on the bodies' own order (one GPU); sorted steps always do
     int sym_small;                //    which kernel takes those steps: 2 the warp-level one (default), 1 the CTA-level one
     int symw_grid;                //    grid of the warp-level kernel (CTAs of 128 threads)
+    int symw_queue;               //    1: its warps take work items from an atomic counter instead of round robin (measurements)
+    int symw_run;                 //    > 0: chunks per work item, instead of the plan's choice (measurements)
     int sym_rows;                 //    rows per lane: 4 (default), 8 (NB_FLAG_SYM_ROWS8)
 };
 
@@ -201,9 +203,10 @@ inline void count_launch(int k = 1) { launch_counter() += k; }
 
 
 // ---- warp-level two-sided kernel: its work queue (shared with the plan) ------------------------------------------
-// Queue ids -> (group, first chunk slot).  Group g needs the chunk slots s0(g) = floor(2 g / run) .. S - 1; pairing g
-// with G - 1 - g makes (almost) equal-length rows of L ids each, so an id decodes with one division; ids that fall off
-// the end of a row pair are void (at most one per row).
+// Work item ids.  First the 2 G "own" items (group g against one of the two chunks that make it up: they cost several
+// times a normal item because every row meets itself there, so they are handed out first), then the triangle proper:
+// group g against the chunk slots s0(g) = floor((2 g + 2) / run) .. S - 1; pairing g with G - 1 - g makes (almost)
+// equal-length rows of L ids each, so an id decodes with one division; ids that fall off the end of a row pair are void.
 struct WGeom {
     int G, C, S, run, L, ids;
 };
@@ -214,8 +217,9 @@ __host__ __device__ inline WGeom symw_geom(int n, int run)
     w.C = (n + kWChunk - 1) / kWChunk;
     w.run = run;
     w.S = (w.C + run - 1) / run;
-    w.L = 2 * w.S - (2 * w.G - 2) / run + (run > 2 ? 1 : 0);     // run <= 2: the two floors are exact
-    w.ids = ((w.G + 1) / 2) * w.L;
+    w.L = 2 * w.S - (2 * w.G + 2) / run + 2;      // an upper bound of every row pair's length (floors, empty last rows)
+    if (w.L < 1) w.L = 1;
+    w.ids = 2 * w.G + ((w.G + 1) / 2) * w.L;
     return w;
 }
 // chunks per work item for n bodies on `warps` resident warps: the longest run that still leaves >= 12 items per warp

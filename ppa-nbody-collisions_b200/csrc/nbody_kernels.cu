@@ -80,7 +80,7 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     if (p.sym && p.coverage == NB_COVERAGE_FULL && small && p.sym_small == 2 &&
         sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
         d.sym = 2;
-        d.sym_S = symw_run(n, 4 * (p.symw_grid > 0 ? p.symw_grid : 1));
+        d.sym_S = p.symw_run > 0 ? p.symw_run : symw_run(n, 4 * (p.symw_grid > 0 ? p.symw_grid : 1));
         d.sym_items = symw_geom(n, d.sym_S).ids;
     } else if (p.sym && p.coverage == NB_COVERAGE_FULL && (d.sorted || (small && p.sym_small == 1 && n >= 2 * kTJ)) &&
         sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {

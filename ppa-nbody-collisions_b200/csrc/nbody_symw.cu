@@ -26,26 +26,34 @@ namespace {
 constexpr int kWThreads = 128;                 // 4 independent warps per CTA
 constexpr int kWIpt = kWGroup / 32;            // rows per lane
 
-__device__ __forceinline__ bool symw_decode(const WGeom &w, const int id, int &g, int &s)
+// id -> group g and chunk range [c_lo, c_hi); false: a void id
+__device__ __forceinline__ bool symw_decode(const WGeom &w, int id, int &g, int &c_lo, int &c_hi)
 {
+    if (id < 2 * w.G) {                        // an own item: one chunk
+        g = id >> 1;
+        c_lo = 2 * g + (id & 1);
+        c_hi = min(c_lo + 1, w.C);
+        return c_lo < w.C;
+    }
+    id -= 2 * w.G;
     const int pi = id / w.L;
-    int off = id - pi * w.L;
-    const int s0a = (2 * pi) / w.run, na = w.S - s0a;
+    int off = id - pi * w.L, s;
+    const int s0a = (2 * pi + 2) / w.run, na = max(w.S - s0a, 0);
+    const int gb = w.G - 1 - pi;
     if (off < na) {
         g = pi;
         s = s0a + off;
-        return true;
-    }
-    off -= na;
-    const int gb = w.G - 1 - pi;
-    if (gb == pi) return false;
-    const int s0b = (2 * gb) / w.run, nb_ = w.S - s0b;
-    if (off < nb_) {
+    } else {
+        off -= na;
+        if (gb == pi) return false;
+        const int s0b = (2 * gb + 2) / w.run;
+        if (off >= w.S - s0b) return false;       // (also when that row is empty: S - s0b <= 0)
         g = gb;
         s = s0b + off;
-        return true;
     }
-    return false;
+    c_lo = max(s * w.run, 2 * g + 2);
+    c_hi = min((s + 1) * w.run, w.C);
+    return c_lo < c_hi;
 }
 
 // the flagged (lane, sub-step) pairs of one round, exactly (see sym_redo in nbody_sym.cu; here radii and indices are at hand)
@@ -121,16 +129,21 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
     const float Rb = sqrtf((4.f * rmax * rmax + p.soft2) * 1.001f);     // no pre-test can pass beyond this separation
     unsigned n_rounds = 0, n_redo = 0, n_culled = 0;
 
-    // the next id is fetched while the current item is being worked on
-    unsigned next = 0;
-    if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+    // Work distribution: ids from an atomic counter, the next one fetched while the current item is being worked on.  The
+    // expensive own items have the lowest ids, so they start first and the queue evens out the rest.  (p.symw_queue = 0
+    // deals the ids round robin instead, warp w taking w, w + W, ...: a measurement knob.)
+    const unsigned total_warps = gridDim.x * (kWThreads / 32), my_warp = blockIdx.x * (kWThreads / 32) + (threadIdx.x >> 5);
+    const bool queue = p.symw_queue != 0;
+    unsigned next = my_warp;
+    if (queue && lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
 #pragma unroll 1
     for (;;) {
-        const unsigned id = __shfl_sync(0xffffffffu, next, 0);
+        const unsigned id = queue ? __shfl_sync(0xffffffffu, next, 0) : next;
         if (id >= (unsigned)w.ids) break;
-        if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
-        int g, s;
-        if (!symw_decode(w, (int)id, g, s)) continue;
+        if (!queue) next += total_warps;
+        else if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+        int g, c_lo, c_hi;
+        if (!symw_decode(w, (int)id, g, c_lo, c_hi)) continue;
         const int rbase = kWGroup * g;
         float nx[kWIpt], ny[kWIpt], nm[kWIpt], ri[kWIpt], thr[kWIpt];
         int oi4[kWIpt];
@@ -167,7 +180,6 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
             const float4 b0 = bx[0], b1 = bx[1];
             rb = make_float4(fminf(b0.x, b1.x), fminf(b0.y, b1.y), fmaxf(b0.z, b1.z), fmaxf(b0.w, b1.w));
         }
-        const int c_lo = max(s * w.run, 2 * g), c_hi = min((s + 1) * w.run, w.C);
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
             const bool own = (c >> 1) == g;
