@@ -6,8 +6,9 @@
  * Same public surface: members X, Y and Element[2]; an uninitialised default constructor, a
  * broadcasting scalar constructor (so `force = 0.f` zeroes both lanes, src/nbody.cu:153), element-wise
  * `*`, `+`, `-`, unary `-`, scalar `*` on both sides, the compound forms, and length().
- * Same arithmetic where it is observable: `v / s` multiplies by a SINGLE-PRECISION reciprocal
- * `1.0f / s` -- also for Vec2<double>, as the reference does (vec2.h:49) -- and length() is
+ * Same arithmetic where it is observable: `v / s` multiplies by the reciprocal `1.0f / s`, rounded once in T
+ * (for Vec2<double> the float literal is promoted and the division is a double division, exactly as in the
+ * reference, vec2.h:49) -- reciprocal-then-multiply, not a division per component -- and length() is
  * sqrt(X*X + Y*Y) evaluated in T.  Dividing by zero asserts (vec2f.h:51) unless NDEBUG is set.
  *
  * The SoA device store of the library (float4 {x,y,m,r}, float2 v) does not use this type; the
@@ -54,7 +55,7 @@ struct Vec2T {
     NB_HD Vec2T operator/(T s) const
     {
         assert(s != 0.0);
-        return *this * (T)(1.0f / s);                            /* reciprocal first, in float */
+        return *this * (T)(1.0f / s);                            /* reciprocal first, evaluated in T */
     }
 
     NB_HD Vec2T &operator*=(T s) { return *this = *this * s; }

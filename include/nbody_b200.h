@@ -78,26 +78,29 @@ typedef struct nb_params {
 #define NB_FLAG_NO_GRAPH 1    /* launch kernels one by one instead of replaying a CUDA graph        */
 #define NB_FLAG_SCALAR_FORCE 2/* use the scalar-FP32 force kernel instead of the packed f32x2 one   */
 #define NB_FLAG_NO_SORT 4     /* never use the cell-sorted shadow order.  By default, with NB_COVERAGE_FULL and
-                                 n >= sort_min_n, every step runs on a Morton-cell-sorted copy of the bodies so that
-                                 the collision pre-test is skipped for (rows, j part) pairs whose bounding boxes are
-                                 apart; results keep the bodies' own order, events and survivors are unchanged     */
+                                 n >= sort_min_n, every step runs on a Morton-cell-sorted copy of the bodies (sorted every 32
+                                 steps, carried over the compaction in between) so that the collision pre-test is skipped
+                                 where bounding boxes are apart; results keep the bodies' own order, events and survivors
+                                 are unchanged                                                                       */
 #define NB_FLAG_MERGE_CONSERVING 16 /* opt-in physics beyond parity (every force path, any number of GPUs): instead of the reference's "heavier
                                  absorbs, nothing is conserved" rule (src/nbody.cu:215-226), every body points at the
                                  lowest index among itself and its hit partners; following the pointers ends at a root,
                                  which takes mass, momentum (at the post-force velocities) and growth * radius of
                                  everything that ends at it, in ascending index order, keeps its position and moves on
                                  with P / M; the others are removed.  Events: kind = ABSORB when i < j, else KILLED   */
-#define NB_FLAG_ONE_SIDED 32   /* never use the two-sided force kernel (below)                                      */
-#define NB_FLAG_PAIR_HALVING 64 /* steps that run on the cell-sorted order (single GPU) evaluate every unordered pair
-                                 once and apply the force to both bodies (Newton's third law): 12 instead of 2 x 9
-                                 packed operations per pair of interactions.  The collision predicate is symmetric bit
-                                 for bit (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged;
-                                 force sums differ from the one-sided kernel only in rounding and summation order, and
-                                 are deterministic (every partial sum has one writer and a fixed order)            */
-#define NB_FLAG_SYM_ROWS8 128  /* tuning variant of the two-sided kernel: 8 rows per lane at 2 CTAs per SM (half the
-                                 shuffles per evaluation).  Same results as the default (4 rows, 3 CTAs); measured 3 %
-                                 slower at n = 262 144 (profiles/r01_two_sided_rows8.log) although the bare loop is 7 %
-                                 faster: kept for tuning, never selected by default                                  */
+#define NB_FLAG_ONE_SIDED 32   /* never use the two-sided force kernels: the ONLY switch of that path.  By default every step
+                                 with NB_COVERAGE_FULL and n >= 12288 (one GPU: a warp per work item below 40960 bodies, a CTA
+                                 per tile pair from there on; several GPUs: the latter) evaluates every unordered pair once
+                                 and applies the force to both bodies (Newton's third law): 12 instead of 2 x 9 packed
+                                 operations per pair of interactions.  The collision predicate is symmetric bit for bit
+                                 (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged; the force
+                                 sums are exact 64-bit fixed-point integers, hence deterministic and the same on any
+                                 number of GPUs                                                                      */
+#define NB_FLAG_PAIR_HALVING 64 /* accepted and ignored: the two-sided kernels are the default (see NB_FLAG_ONE_SIDED)    */
+#define NB_FLAG_SYM_ROWS8 128  /* tuning variant of the CTA-level two-sided kernel: 8 rows per lane at 2 CTAs per SM (half the
+                                 shuffles per evaluation).  Same results as the default (4 rows, 3 CTAs); measured 1 %
+                                 slower at n = 1 048 576 and 20 % slower at n = 70 000 (profiles/r02_rows4_vs_rows8.jsonl):
+                                 kept for tuning, never selected by default                                          */
 #define NB_SORT_MIN_N_DEFAULT 12288
 #define NB_FLAG_VARIANT_SHIFT 8   /* bits 8..11: force-kernel variant (occupancy / rows-per-lane trade-off,
                                      see nbody_kernels.cu); 0 = default                                */
@@ -149,7 +152,8 @@ int  nb_version(void);
  * resets the step counter, statistics and event log.  nb_download replaces the
  * D2H copy + host compaction of src/nbody.cu:486-510: it returns the already
  * compacted survivors in the same layout (re-laid-out for the current n).
- * Every rank of a sharded run uploads the same full block.
+ * Every rank of a sharded run passes the same full block; after nb_comm_init each rank copies only its 1 / world of
+ * every array over PCIe and the rest arrives from the peers over NVLink.
  */
 int nb_upload(nb_ctx *ctx, const void *bodies, int n);
 int nb_download(nb_ctx *ctx, void *bodies, int capacity_n, int *n);
@@ -182,9 +186,12 @@ int nb_events(nb_ctx *ctx, nb_event *buf, int capacity, int *count);
 /* ---- multi-GPU (one process per GPU) ------------------------------------ */
 /*
  * Rank 0 calls nb_comm_unique_id (128 bytes, an ncclUniqueId), the host
- * distributes it (e.g. torch.distributed / MPI broadcast), then every rank
- * calls nb_comm_init.  After that nb_step exchanges the shard results with one
- * ncclAllGather per step over NVLink.
+ * distributes it (threads of one process: shared memory, as `nbody --gpus N` does;
+ * processes: e.g. a torch.distributed / MPI broadcast), then every rank calls
+ * nb_comm_init.  After that nb_step exchanges the shard results over NVLink:
+ * one ncclAllGather of the post-step rows per step, plus -- two-sided steps --
+ * one integer ncclAllReduce of the fixed-point force sums and one
+ * ncclAllGather of the candidate pairs.
  */
 #define NB_UNIQUE_ID_BYTES 128
 int nb_comm_unique_id(void *id_out);

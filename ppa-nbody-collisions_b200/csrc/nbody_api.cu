@@ -259,6 +259,8 @@ int nb_create(nb_ctx **out, const nb_params *params)
                 sp.sym_min_n = kSymMinNDefault;
                 sp.sym_small = 2;
                 sp.symw_queue = 1;
+                sp.symw_max_n = kSymWarpMaxN;
+                if (const char *e = getenv("NBODY_B200_SYMW_MAX_N")) sp.symw_max_n = atoi(e);         // tuning only
                 if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);       // tuning only
                 if (const char *e = getenv("NBODY_B200_SYM_SMALL")) sp.sym_small = atoi(e) == 1 ? 1 : 2;
                 if (const char *e = getenv("NBODY_B200_SYMW_QUEUE")) sp.symw_queue = atoi(e) != 0;
@@ -812,6 +814,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     sp.sym_grid = (sp.sym_rows == 8 ? 2 : 3) * 148; // the queue granularity rule (sym_lgu) is quoted for a B200
     sp.sym_min_n = sp.world == 1 ? kSymMinNDefault : 0;
     sp.sym_small = 2;
+    sp.symw_max_n = kSymWarpMaxN;
     sp.symw_grid = 6 * 148;
     sp.field_w = sp.field_h = 1;
     {

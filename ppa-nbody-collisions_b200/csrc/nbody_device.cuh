@@ -126,6 +126,7 @@ struct StepParams {
     int sym_min_n;                //    smallest n that runs it on the bodies' own order (one GPU); sorted steps always do
     int sym_small;                //    which kernel takes those steps: 2 the warp-level one (default), 1 the CTA-level one
     int symw_grid;                //    grid of the warp-level kernel (CTAs of 128 threads)
+    int symw_max_n;               //    the warp-level kernel takes steps with sym_min_n <= n < symw_max_n
     int symw_queue;               //    1: its warps take work items from an atomic counter instead of round robin (measurements)
     int symw_run;                 //    > 0: chunks per work item, instead of the plan's choice (measurements)
     int sym_rows;                 //    rows per lane: 4 (default), 8 (NB_FLAG_SYM_ROWS8)

@@ -29,7 +29,10 @@
 //                        two-sided kernel (all-pairs coverage from 40960 bodies on): its force sums are exact integers
 #include <sys/time.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -141,7 +144,14 @@ int main(int argc, char **argv)
 
     if (gpus < 1) gpus = 1;
     unsigned char comm_id[NB_UNIQUE_ID_BYTES];
+    std::atomic<int> comm_ready{0};
+    int saved_stdout = -1;
     if (gpus > 1) {
+        // NCCL may print its version banner on stdout while the communicator is set up; stdout is the reference's
+        // output format, so it points at stderr until every rank has joined
+        fflush(stdout);
+        saved_stdout = dup(1);
+        dup2(2, 1);
         const int rc = nb_comm_unique_id(comm_id);
         if (rc != NB_OK) die(nullptr, "nb_comm_unique_id", rc);
     }
@@ -169,7 +179,16 @@ int main(int argc, char **argv)
         nb_ctx *ctx = nullptr;
         int rc = nb_create(&ctx, &par);
         if (rc != NB_OK) die(nullptr, "nb_create", rc);
-        if (gpus > 1 && (rc = nb_comm_init(ctx, comm_id)) != NB_OK) die(ctx, "nb_comm_init", rc);
+        if (gpus > 1) {
+            if ((rc = nb_comm_init(ctx, comm_id)) != NB_OK) die(ctx, "nb_comm_init", rc);
+            ++comm_ready;
+            if (rank == 0) {
+                while (comm_ready.load() < gpus) std::this_thread::yield();
+                fflush(stdout);
+                dup2(saved_stdout, 1);
+                close(saved_stdout);
+            }
+        }
         if ((rc = nb_upload(ctx, block.data(), n0)) != NB_OK) die(ctx, "nb_upload", rc);
 
         const bool lead = rank == 0;
