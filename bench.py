@@ -329,8 +329,8 @@ def parity_one_gpu(nb, sim, cfg, n_rows=160) -> dict:
 
 def parity_sharded(nb, sim, cfg, block0, dist, rank, world, local, sim_steps: int) -> dict:
     """The sharded run's state after the timed steps: replicas bit-identical, and -- rank 0 repeats the same number
-    of steps from the same bodies on ONE GPU -- events, survivors, masses and radii identical, velocities within
-    1e-4 max|v| (the two runs add the same forces in a different order)."""
+    of steps from the same bodies on ONE GPU -- events, survivors, masses and radii identical; velocities are bounded
+    by 1e-4 max|v| here, and in fact identical bit for bit whenever the two-sided kernel ran (integer force sums)."""
     got, n1 = sim.download()
     ev = sim.events()
     st = sim.stats()
@@ -341,31 +341,39 @@ def parity_sharded(nb, sim, cfg, block0, dist, rank, world, local, sim_steps: in
     dist.all_gather_object(all_ev, ev)
     res = None
     if rank == 0:
-        n, field = cfg["n"], cfg["field"]
-        cov = nb.COVERAGE_FULL if cfg["coverage"] == "full" else nb.COVERAGE_REFERENCE
-        one = nb.Simulation(n, field_w=field, field_h=field, coverage=cov, device=local, event_capacity=1 << 22)
-        one.upload(block0, n)
-        one.step(sim_steps)
-        ref, n_ref = one.download()
-        ev_ref = one.events()
-        one.close()
-        evs = np.concatenate(all_ev)
-        evs = evs[np.lexsort((evs["i"], evs["step"]))]      # stable: a row's events stay in visit order
-        ev_ok = len(evs) == len(ev_ref) and all(np.array_equal(evs[k], ev_ref[k]) for k in ("step", "i", "j", "kind"))
-        res = {"checked": True, "against": f"the same {sim_steps} steps on one GPU (rank 0), whole state",
-               "sim_steps": sim_steps, "replicas_identical": len({(d[0], d[1]) for d in all_d}) == 1,
-               "state_crc32": [d[1] for d in all_d], "bodies_after": [d[0] for d in all_d], "bodies_after_1gpu": int(n_ref),
-               "events": int(len(evs)), "events_vs_1gpu": bool(ev_ok), "overflow": [d[3] for d in all_d],
-               "events_dropped": [d[4] for d in all_d], "survivors_vs_1gpu": bool(n1 == n_ref)}
-        if n1 == n_ref:
-            _, v1, m1, r1 = nb.split(got, n1)
-            _, v2, m2, r2 = nb.split(ref, n_ref)
-            res["mass_radius_bits_vs_1gpu"] = bool(np.array_equal(m1.view(np.uint32), m2.view(np.uint32))
-                                                   and np.array_equal(r1.view(np.uint32), r2.view(np.uint32)))
-            res["dv_rel_max_vs_1gpu"] = float(np.abs(v1 - v2).max() / max(float(np.abs(v2).max()), 1e-30))
-        res["ok"] = bool(res["replicas_identical"] and res["events_vs_1gpu"] and res["survivors_vs_1gpu"]
-                         and res.get("mass_radius_bits_vs_1gpu", False) and res.get("dv_rel_max_vs_1gpu", 1.0) <= 1e-4
-                         and not any(res["overflow"]) and not any(res["events_dropped"]))
+        try:                                       # a failed check must not leave the other ranks waiting in a collective
+            res = _parity_vs_one_gpu(nb, cfg, block0, local, sim_steps, got, n1, all_d, all_ev)
+        except Exception as e:                     # noqa: BLE001
+            res = {"checked": False, "ok": False, "why": f"{type(e).__name__}: {e}"}
+    return res
+
+
+def _parity_vs_one_gpu(nb, cfg, block0, local, sim_steps, got, n1, all_d, all_ev) -> dict:
+    n, field = cfg["n"], cfg["field"]
+    cov = nb.COVERAGE_FULL if cfg["coverage"] == "full" else nb.COVERAGE_REFERENCE
+    one = nb.Simulation(n, field_w=field, field_h=field, coverage=cov, device=local, event_capacity=1 << 22)
+    one.upload(block0, n)
+    one.step(sim_steps)
+    ref, n_ref = one.download()
+    ev_ref = one.events()
+    one.close()
+    evs = np.concatenate(all_ev)
+    evs = evs[np.lexsort((evs["i"], evs["step"]))]      # stable: a row's events stay in visit order
+    ev_ok = len(evs) == len(ev_ref) and all(np.array_equal(evs[k], ev_ref[k]) for k in ("step", "i", "j", "kind"))
+    res = {"checked": True, "against": f"the same {sim_steps} steps on one GPU (rank 0), whole state",
+           "sim_steps": sim_steps, "replicas_identical": len({(d[0], d[1]) for d in all_d}) == 1,
+           "state_crc32": [d[1] for d in all_d], "bodies_after": [d[0] for d in all_d], "bodies_after_1gpu": int(n_ref),
+           "events": int(len(evs)), "events_vs_1gpu": bool(ev_ok), "overflow": [d[3] for d in all_d],
+           "events_dropped": [d[4] for d in all_d], "survivors_vs_1gpu": bool(n1 == n_ref)}
+    if n1 == n_ref:
+        _, v1, m1, r1 = nb.split(got, n1)
+        _, v2, m2, r2 = nb.split(ref, n_ref)
+        res["mass_radius_bits_vs_1gpu"] = bool(np.array_equal(m1.view(np.uint32), m2.view(np.uint32))
+                                               and np.array_equal(r1.view(np.uint32), r2.view(np.uint32)))
+        res["dv_rel_max_vs_1gpu"] = float(np.abs(v1 - v2).max() / max(float(np.abs(v2).max()), 1e-30))
+    res["ok"] = bool(res["replicas_identical"] and res["events_vs_1gpu"] and res["survivors_vs_1gpu"]
+                     and res.get("mass_radius_bits_vs_1gpu", False) and res.get("dv_rel_max_vs_1gpu", 1.0) <= 1e-4
+                     and not any(res["overflow"]) and not any(res["events_dropped"]))
     return res
 
 
@@ -523,7 +531,10 @@ def main() -> int:
         e2e_steps = max(1, args.steps)
         sim.upload_ptr(host_in.data_ptr(), n)
         sim.step(batch)
-        sim.download_ptr(host_out.data_ptr(), n)            # warm
+        if rank == 0:
+            sim.download_ptr(host_out.data_ptr(), n)        # warm
+        else:
+            sim.sync()
         barrier()
         d2h = 0
         pairs_e2e = 0.0
@@ -535,7 +546,11 @@ def main() -> int:
             tb = time.perf_counter()
             sim.step(batch)
             tc = time.perf_counter()
-            n_out = sim.download_ptr(host_out.data_ptr(), n)
+            if rank == 0:                   # the replicas hold the same bodies: ONE copy of the result goes back to the host
+                n_out = sim.download_ptr(host_out.data_ptr(), n)
+            else:
+                sim.sync()
+                n_out = 0
             td = time.perf_counter()
             phase[0] += tb - ta
             phase[1] += tc - tb
@@ -554,7 +569,9 @@ def main() -> int:
                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
                "host_ms_per_step": {"nb_upload": phase[0] / e2e_steps * 1e3, "nb_step": phase[1] / e2e_steps * 1e3,
                                     "nb_download": phase[2] / e2e_steps * 1e3, "rank": 0},
-               "what": f"nb_upload(pinned host block) + nb_step({batch}) + nb_download(pinned host block) per step, wall clock"}
+               "what": (f"nb_upload(pinned host block) + nb_step({batch}) + nb_download(pinned host block) per step, wall clock"
+                        + ("; every rank uploads (1 / world of the block over PCIe each, the rest over NVLink), rank 0 downloads the "
+                           "one copy of the result the job needs (the replicas are identical)" if world > 1 else ""))}
 
     # ---- the configuration's whole run (BASELINE: "1000 steps", "2000 iterations", ...), timed once as an extra --------
     whole = None

@@ -286,7 +286,10 @@ class Simulation:
         self._check("nb_get_stats", lib().nb_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
-    def events(self, capacity: int = 1 << 20) -> np.ndarray:
+    def events(self, capacity: int | None = None) -> np.ndarray:
+        """All records logged since the last call (nb_events).  The default buffer holds the whole log (event_capacity)."""
+        if capacity is None:
+            capacity = max(int(self.params.event_capacity), 1)
         buf = np.zeros(capacity, dtype=EVENT_DTYPE)
         cnt = C.c_int(0)
         self._check("nb_events", lib().nb_events(self._h, buf.ctypes.data, capacity, C.byref(cnt)))
