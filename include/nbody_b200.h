@@ -89,8 +89,8 @@ typedef struct nb_params {
                                  everything that ends at it, in ascending index order, keeps its position and moves on
                                  with P / M; the others are removed.  Events: kind = ABSORB when i < j, else KILLED   */
 #define NB_FLAG_ONE_SIDED 32   /* never use the two-sided force kernels: the ONLY switch of that path.  By default every step
-                                 with NB_COVERAGE_FULL and n >= 12288 (one GPU: a warp per work item below 40960 bodies, a CTA
-                                 per tile pair from there on; several GPUs: the latter) evaluates every unordered pair once
+                                 with NB_COVERAGE_FULL and n >= 12288 (a warp per work item below 196608 bodies, a CTA
+                                 per tile pair from there on) evaluates every unordered pair once
                                  and applies the force to both bodies (Newton's third law): 12 instead of 2 x 9 packed
                                  operations per pair of interactions.  The collision predicate is symmetric bit for bit
                                  (src/nbody.cu:126-134), so events, survivors, masses and radii are unchanged; the force

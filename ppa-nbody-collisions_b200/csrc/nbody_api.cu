@@ -255,19 +255,17 @@ int nb_create(nb_ctx **out, const nb_params *params)
         if (socc > 0) {
             sp.sym = 1;
             sp.sym_grid = c->sm_count * socc;
-            if (world == 1) {
-                sp.sym_min_n = kSymMinNDefault;
-                sp.sym_small = 2;
-                sp.symw_queue = 1;
-                sp.symw_max_n = kSymWarpMaxN;
-                if (const char *e = getenv("NBODY_B200_SYMW_MAX_N")) sp.symw_max_n = atoi(e);         // tuning only
-                if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);       // tuning only
-                if (const char *e = getenv("NBODY_B200_SYM_SMALL")) sp.sym_small = atoi(e) == 1 ? 1 : 2;
-                if (const char *e = getenv("NBODY_B200_SYMW_QUEUE")) sp.symw_queue = atoi(e) != 0;
-                if (const char *e = getenv("NBODY_B200_SYMW_RUN")) sp.symw_run = atoi(e) > 0 ? atoi(e) : 0;
-                int wregs = 0;
-                sp.symw_grid = c->sm_count * std::max(1, force_symw_occupancy(&wregs));
-            }
+            sp.sym_min_n = kSymMinNDefault;
+            sp.sym_small = 2;
+            sp.symw_queue = 1;
+            sp.symw_max_n = kSymWarpMaxN;
+            if (const char *e = getenv("NBODY_B200_SYM_MIN_N")) sp.sym_min_n = atoi(e);           // tuning only
+            if (const char *e = getenv("NBODY_B200_SYMW_MAX_N")) sp.symw_max_n = atoi(e);
+            if (const char *e = getenv("NBODY_B200_SYM_SMALL")) sp.sym_small = atoi(e) == 1 ? 1 : 2;
+            if (const char *e = getenv("NBODY_B200_SYMW_QUEUE")) sp.symw_queue = atoi(e) != 0;
+            if (const char *e = getenv("NBODY_B200_SYMW_RUN")) sp.symw_run = atoi(e) > 0 ? atoi(e) : 0;
+            int wregs = 0;
+            sp.symw_grid = c->sm_count * std::max(1, force_symw_occupancy(&wregs));
         }
     }
     sp.lg_parts_override = -1;
@@ -812,7 +810,7 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
               ((params->flags & NB_FLAG_PAIR_HALVING) || kPairHalvingDefault) && (sp.sort_min_n > 0 || sp.world == 1)) ? 1 : 0;
     sp.sym_rows = (params->flags & NB_FLAG_SYM_ROWS8) ? 8 : 4;
     sp.sym_grid = (sp.sym_rows == 8 ? 2 : 3) * 148; // the queue granularity rule (sym_lgu) is quoted for a B200
-    sp.sym_min_n = sp.world == 1 ? kSymMinNDefault : 0;
+    sp.sym_min_n = kSymMinNDefault;
     sp.sym_small = 2;
     sp.symw_max_n = kSymWarpMaxN;
     sp.symw_grid = 6 * 148;

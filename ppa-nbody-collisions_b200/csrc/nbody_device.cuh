@@ -44,7 +44,8 @@ constexpr int kResortEvery = 32;             // the cell-sorted order is rebuilt
 constexpr int kSymSMax = 8;                  // two-sided force kernel: a block of the pair triangle is S x S tile pairs, S <= 8
 constexpr int kSymMinNDefault = 12288;       // smallest n the warp-level two-sided kernel takes (one GPU); below it the one-sided
                                              // kernel is faster (profiles/r02_small_n_sweep.md)
-constexpr int kSymWarpMaxN = 40960;          // from here on the CTA-level kernel of nbody_sym.cu takes over
+constexpr int kSymWarpMaxN = 196608;         // from here on the CTA-level kernel of nbody_sym.cu takes over (the warp-level one is
+                                             // 21 % / 11 % faster at n = 65 536 / 131 072, 2 % / 4 % slower at 262 144 / 1M)
 constexpr int kWGroup = 128;                 // warp-level two-sided kernel (nbody_symw.cu): rows per group, bodies per chunk
 constexpr int kWChunk = 64;
 constexpr float kPadCoord = 1.0e18f;         // padding j bodies sit here: d2 ~ 2e36, finite, contributes exactly 0

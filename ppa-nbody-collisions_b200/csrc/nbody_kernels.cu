@@ -76,7 +76,8 @@ __host__ __device__ inline void plan_fill(StepDesc &d, const StepParams &p, int 
     // Two-sided kernels (all-pairs coverage, a fixed-point scale for the force sums must exist; else the one-sided kernel
     // runs).  One GPU, sym_min_n <= n < kSymWarpMaxN: a warp per work item (nbody_symw.cu), on the sorted order if the step
     // has one.  Otherwise, on the sorted order: a CTA per tile pair (nbody_sym.cu).
-    const bool small = p.world <= 1 && p.sym_min_n > 0 && n >= p.sym_min_n && n < p.symw_max_n;
+    // (several GPUs: only on the sorted order -- the plain step graph holds no exchange of force sums and candidates)
+    const bool small = p.sym_min_n > 0 && n >= p.sym_min_n && n < p.symw_max_n && (p.world <= 1 || d.sorted);
     if (p.sym && p.coverage == NB_COVERAGE_FULL && small && p.sym_small == 2 &&
         sym_scale(n, mmax, rmin, p.field_w > p.field_h ? p.field_w : p.field_h, &d.fscale, &d.finv)) {
         d.sym = 2;

@@ -14,7 +14,7 @@
 //   --softening EPS      opt-in Plummer softening length for the forces (not reference behaviour)
 //   --merge MODE         reference (default, src/nbody.cu:215-226) | conserving (opt-in lowest-index merge that
 //                        conserves mass and momentum; not reference behaviour)
-//   --one-sided          never use the two-sided (pair-halving) force kernel (full coverage, >= 40960 bodies)
+//   --one-sided          never use the two-sided (pair-halving) force kernel (full coverage, >= 12288 bodies)
 //   --no-images          skip rendering and image files
 //   --render MODE        reference (default: the bodies the reference's stale launch grid draws, src/nbody.cu:473,535:
 //                        those below 128 * floor(n_before_the_step / 128)) | all (every live body)
@@ -26,7 +26,7 @@
 //   --gpus N             shard the step over N GPUs of this node: one host thread and one library context per GPU
 //                        (devices D .. D + N - 1), NCCL between them (nb_comm_unique_id / nb_comm_init).  Rank 0 prints,
 //                        draws and dumps; the event list is merged from all ranks.  Results do not depend on N for the
-//                        two-sided kernel (all-pairs coverage from 40960 bodies on): its force sums are exact integers
+//                        two-sided kernel (all-pairs coverage from 12288 bodies on): its force sums are exact integers
 #include <sys/time.h>
 
 #include <unistd.h>

@@ -25,9 +25,6 @@ __device__ __forceinline__ long long to_fixed(float v, float fscale) { return __
 // fetched instructions; the back-edge of a partially unrolled loop costs register moves).  The warp-level kernel must
 // not: its 24 warps per SM are all in different places, and 47 KB of straight-line code per round thrash the
 // instruction cache (ncu: 3 warps stalled on "no instruction" per issue, profiles/r02_force_16k_warp_level_unrolled_ncu.json).
-#ifndef NB_SYM_UV
-#define NB_SYM_UV 0
-#endif
 template <bool TEST, int IPT, int UNROLL = 32>
 __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms, float2 &gx, float2 &gy,
                                              const float (&nx)[IPT], const float (&ny)[IPT],
@@ -51,22 +48,12 @@ __device__ __forceinline__ void sym_substeps(float2 &xs, float2 &ys, float2 &ms,
                 i3.y = f1 ? 0.f : i3.y;
                 flagged |= f0 | f1;
             }
-#if NB_SYM_UV
-            // direction first: the two j-side accumulates then take the row's mass as a SCALAR operand, which leaves only two
-            // packed FMAs per evaluation with three distinct register pairs (operand-fetch bound, profiles/r01_bank_probe.jsonl)
-            const float2 u = __fmul2_rn(dx, i3), v = __fmul2_rn(dy, i3);
-            tfx[q] = __ffma2_rn(u, ms, tfx[q]);
-            tfy[q] = __ffma2_rn(v, ms, tfy[q]);
-            gx = __ffma2_rn(u, make_float2(nm[q], nm[q]), gx);
-            gy = __ffma2_rn(v, make_float2(nm[q], nm[q]), gy);
-#else
             const float2 sj = __fmul2_rn(i3, ms);
             const float2 si = __fmul2_rn(i3, make_float2(nm[q], nm[q]));
             tfx[q] = __ffma2_rn(dx, sj, tfx[q]);
             tfy[q] = __ffma2_rn(dy, sj, tfy[q]);
             gx = __ffma2_rn(dx, si, gx);
             gy = __ffma2_rn(dy, si, gy);
-#endif
         }
         if (TEST) mask |= flagged ? (1u << s) : 0u;
         xs.x = __shfl_sync(0xffffffffu, xs.x, src);

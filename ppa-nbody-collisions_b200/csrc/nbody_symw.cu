@@ -57,7 +57,7 @@ __device__ __forceinline__ bool symw_decode(const WGeom &w, int id, int &g, int 
 }
 
 // the flagged (lane, sub-step) pairs of one round, exactly (see sym_redo in nbody_sym.cu; here radii and indices are at hand)
-__device__ __forceinline__ void symw_redo(const DevState &st, const int rbase, const int cbase, const bool own,
+__device__ __forceinline__ void symw_redo(const DevState &st, const int rank, const int rbase, const int cbase, const bool own,
                                           const float soft2, const unsigned mask, const float2 xs, const float2 ys,
                                           const float2 ms, const float2 rj, const int2 oj2, const int (&oi4)[kWIpt], float2 &gx, float2 &gy,
                                           const float (&nx)[kWIpt], const float (&ny)[kWIpt], const float (&nm)[kWIpt],
@@ -92,8 +92,8 @@ __device__ __forceinline__ void symw_redo(const DevState &st, const int rbase, c
                         if (oi < 0 || oj < 0 || is == js) {
                             // padding, or the self pair: nothing
                         } else if (d2 <= rsum * rsum) {           // src/nbody.cu:126-134
-                            push_candidate(st, 0, oi, oj);
-                            if (!own) push_candidate(st, 0, oj, oi);
+                            push_candidate(st, rank, oi, oj);
+                            if (!own) push_candidate(st, rank, oj, oi);
                         } else {
                             const float inv = rsqrt_approx(d2s);
                             const float i3 = (inv * inv) * inv;
@@ -133,15 +133,17 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
     // expensive own items have the lowest ids, so they start first and the queue evens out the rest.  (p.symw_queue = 0
     // deals the ids round robin instead, warp w taking w, w + W, ...: a measurement knob.)
     const unsigned total_warps = gridDim.x * (kWThreads / 32), my_warp = blockIdx.x * (kWThreads / 32) + (threadIdx.x >> 5);
+    // several GPUs: rank r takes ids r, r + world, ... of the same order
     const bool queue = p.symw_queue != 0;
-    unsigned next = my_warp;
-    if (queue && lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+    const unsigned W = (unsigned)p.world, R = (unsigned)p.rank;
+    unsigned next = my_warp * W + R;
+    if (queue && lane == 0) next = atomicAdd(&st.res->sym_next, 1u) * W + R;
 #pragma unroll 1
     for (;;) {
         const unsigned id = queue ? __shfl_sync(0xffffffffu, next, 0) : next;
         if (id >= (unsigned)w.ids) break;
-        if (!queue) next += total_warps;
-        else if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u);
+        if (!queue) next += total_warps * W;
+        else if (lane == 0) next = atomicAdd(&st.res->sym_next, 1u) * W + R;
         int g, c_lo, c_hi;
         if (!symw_decode(w, (int)id, g, c_lo, c_hi)) continue;
         const int rbase = kWGroup * g;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kWThreads, 6) force_symw_kernel(const DevState
             if (may_hit) {
                 sym_substeps<true, kWIpt, UNROLL>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
                 if (__any_sync(0xffffffffu, mask != 0u))
-                    symw_redo(st, rbase, cbase, own, p.soft2, mask, xs, ys, ms, rj, oj2, oi4, gx, gy, nx, ny, nm, ri, thr, tfx, tfy, lane, n_redo);
+                    symw_redo(st, p.rank, rbase, cbase, own, p.soft2, mask, xs, ys, ms, rj, oj2, oi4, gx, gy, nx, ny, nm, ri, thr, tfx, tfy, lane, n_redo);
             } else {
                 sym_substeps<false, kWIpt, UNROLL>(xs, ys, ms, gx, gy, nx, ny, nm, thr, s2, tfx, tfy, mask, lane);
                 ++n_culled;

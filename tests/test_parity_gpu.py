@@ -507,7 +507,7 @@ def test_driver_checkpoint_resume(nb, tmp_path):
 @pytest.mark.parametrize("n,field,sort_min_n,steps", [(1500, 6000, 1024, 6), (3000, 12000, 2900, 6), (16384, 100000, 1024, 10),
                                                       (20000, 60000, 19000, 8)])
 def test_cell_sorted_order(nb, oracle, n, field, sort_min_n, steps):
-    """The cell-sorted shadow order (default from 40 960 bodies on) forced on at small n: same events, survivors,
+    """The cell-sorted shadow order (default from 12 288 bodies on) forced on at small n: same events, survivors,
     masses and radii as the oracle; the second and fourth case cross the threshold while running, so steps on the
     sorted order and on the bodies' own order follow each other in both graphs."""
     block0 = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
@@ -564,7 +564,7 @@ def test_two_sided_on_the_bodies_own_order(nb, oracle, n, field, steps, small, m
 @pytest.mark.parametrize("n,field,steps,scheduled", [(16384, 100000, 40, True), (16384, 45000, 8, False), (20000, 30000, 4, False),
                                                      (33000, 140000, 3, False), (40000, 160000, 3, False)])
 def test_warp_level_kernel_on_the_sorted_order(nb, oracle, n, field, steps, scheduled):
-    """The default path from 12288 to 40960 bodies on one GPU: the cell-sorted order (re-sorted every 32 steps, carried
+    """The default path from 12288 to 196608 bodies: the cell-sorted order (re-sorted every 32 steps, carried
     over the compaction in between) with the warp-per-work-item two-sided kernel, bounding boxes culling the pre-test.
     The first scenario runs 40 steps (across a re-sort), the second and third fall below 12288 bodies while running
     (oracle: 16384 -> ... 12402, 12136 after steps 5, 6; 20000 -> 12020 after the first step): sorted two-sided steps

@@ -106,14 +106,14 @@ def test_two_sided_plan_covers_every_tile_pair_once(nb):
     """Host logic of the two-sided force kernel: which steps use it, the cut of the pair triangle into blocks, and the
     deal of the blocks to the ranks -- every unordered tile pair belongs to exactly one block of exactly one rank."""
     for n, world in ((1023, 1), (12287, 1), (12288, 1), (16384, 1), (16384, 2), (40959, 1), (40959, 2), (40960, 1), (49152, 1), (131072, 1),
-                     (1048576, 1), (4194304, 1), (1000003, 2), (1048576, 8), (4194304, 8), (70000, 3)):
+                     (196607, 1), (196608, 1), (262144, 2), (1048576, 1), (4194304, 1), (1000003, 2), (1048576, 8), (4194304, 8), (70000, 3)):
         plans = [nb.plan(n, coverage=nb.COVERAGE_FULL, rank=r, world=world) for r in range(world)]
         p = plans[0]
-        # the cell-sorted order and a two-sided kernel from 12288 bodies on: on one GPU below 40960 bodies the warp-level
-        # kernel, else the CTA-level kernel whose cut of the pair triangle is checked here
+        # the cell-sorted order and a two-sided kernel from 12288 bodies on: below 196608 bodies the warp-level kernel, from
+        # there on the CTA-level kernel whose cut of the pair triangle is checked here
         uses = n >= 12288
         assert p["sorted"] == int(uses) and p["two_sided"] == int(uses), (n, world, p)
-        if not uses or (world == 1 and n < 40960):
+        if not uses or n < 196608:                 # the warp-level kernel's range (any number of GPUs): no tile-pair cut
             continue
         T, S, Q = p["n_jtiles"], p["sym_S"], p["sym_Q"]
         # the cut depends on the tile count alone (never on the number of GPUs): one GPU and several round alike
@@ -146,8 +146,8 @@ def test_two_sided_plan_covers_every_tile_pair_once(nb):
 
 def test_two_sided_plan_flags(nb):
     assert nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["two_sided"] == 0 and nb.plan(131072, flags=nb.FLAG_ONE_SIDED)["sorted"] == 1
-    # without the sorted order one GPU still runs the warp-level kernel below 40960 bodies (every round pre-tested)
-    assert nb.plan(131072, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(131072, flags=nb.FLAG_NO_SORT)["two_sided"] == 0
+    # without the sorted order one GPU still runs the warp-level kernel below 196608 bodies (every round pre-tested)
+    assert nb.plan(262144, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(262144, flags=nb.FLAG_NO_SORT)["two_sided"] == 0
     assert nb.plan(30000, flags=nb.FLAG_NO_SORT)["sorted"] == 0 and nb.plan(30000, flags=nb.FLAG_NO_SORT)["two_sided"] == 1
     assert nb.plan(30000, flags=nb.FLAG_NO_SORT, world=2)["two_sided"] == 0
     assert nb.plan(131072, coverage=nb.COVERAGE_REFERENCE)["two_sided"] == 0
