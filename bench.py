@@ -28,6 +28,8 @@ at 20 flop per interaction (peak measured in the same run by nb_probe_fp32).  `p
 very state the timed steps produced: sampled rows of one more step against the CPU oracle (1 GPU), replicas
 bit-identical and events / survivors / masses / radii identical to the same steps on ONE GPU (N > 1).
 `cpu_baseline` times the CPU oracle port on the host cores on a bounded sample of rows (N = 1 only).
+The oracle appears here in exactly two roles, both outside every timed region: as the CPU baseline, and as the
+checker behind `parity`.
 
 --impl reference times the UNMODIFIED reference kernels (oracle/_ref, built from /root/reference/src/nbody.cu)
 driven through the reference's own main-loop body on the same GPU: the reference has no CPU implementation

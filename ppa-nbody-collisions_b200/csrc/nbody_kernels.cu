@@ -1073,8 +1073,12 @@ cudaError_t launch_force(const DevState &st, const StepParams &p, int variant, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !p.sym) return e;
     // a context that can run the two-sided kernels: whichever kernel the step descriptor does not name returns at once
-    if (p.sort_min_n > 0 || p.sym_small == 1) e = launch_force_sym(st, p, s);
-    if (e == cudaSuccess && p.sym_small == 2 && p.sym_min_n > 0) e = launch_force_symw(st, p, s);
+    // (a kernel the context's capacity can never reach is not launched at all: n <= n_max)
+    // CTA-level kernel: sorted steps outside the warp-level kernel's range [sym_min_n, symw_max_n)
+    const bool cta_level = p.sym_small == 1 || (p.sort_min_n > 0 && (p.sym_small != 2 || st.cap >= p.symw_max_n || p.sort_min_n < p.sym_min_n));
+    const bool warp_level = p.sym_small == 2 && p.sym_min_n > 0 && st.cap >= p.sym_min_n;
+    if (cta_level) e = launch_force_sym(st, p, s);
+    if (e == cudaSuccess && warp_level) e = launch_force_symw(st, p, s);
     return e;
 }
 

@@ -212,15 +212,19 @@ def _two_sided_worker(rank: int, world: int, port: int, n: int, field: int, out_
                 if fj is not None:
                     F[tile(J)] += fj
                 pairs += pp
-    # the exchange: one all_gather of {partial forces, count, pairs} per rank
+    # the exchange, as the library does it: the forces are 64-bit fixed-point sums (scale 2^k from a bound on |F|: n * m_max /
+    # (2 r_min)^2 * 2^k < 2^62) that meet in ONE integer all-reduce -- exact, so every rank ends with the same bits whatever
+    # the deal -- and the hit pairs travel in one all_gather of {count, pairs} per rank
+    bound = n * float(m.max()) / (4.0 * float(r.min()) ** 2)
+    k = 61 - int(np.floor(np.log2(bound)))
+    fixed = torch.from_numpy(np.rint(np.ldexp(F, k)).astype(np.int64))
+    dist.all_reduce(fixed, op=dist.ReduceOp.SUM)
+    total = np.ldexp(fixed.numpy().astype(np.float64), -k)
     cap = 4 * n
     mine = np.full((cap, 2), -1, dtype=np.int64)
     mine[:len(pairs)] = np.array(pairs, dtype=np.int64).reshape(-1, 2)
-    Fs = [torch.zeros(n, 2, dtype=torch.float64) for _ in range(world)]
     Ps = [torch.zeros(cap, 2, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(Fs, torch.from_numpy(F))
     dist.all_gather(Ps, torch.from_numpy(mine))
-    total = sum(f.numpy() for f in Fs)                                   # rank order, identical on every rank
     allp = np.concatenate([p.numpy() for p in Ps])
     allp = allp[allp[:, 0] >= 0]
     np.savez(os.path.join(out_dir, f"two_sided_{rank}.npz"), F=total, pairs=allp[np.lexsort((allp[:, 1], allp[:, 0]))])
@@ -230,8 +234,9 @@ def _two_sided_worker(rank: int, world: int, port: int, n: int, field: int, out_
 @pytest.mark.parametrize("world,n,field", [(2, 1500, 6000), (3, 2600, 9000), (2, 3000, 6000)])
 def test_two_sided_deal_and_exchange_equal_the_one_sided_sum(oracle, nb, tmp_path, world, n, field):
     """world_size-2 / -3 gloo run of the sharded two-sided flow: blocks of the pair triangle dealt round-robin by the
-    library's plan, every rank's partial forces and hit pairs brought together by one all_gather.  The sum must be the
-    all-pairs force on every body and the union of the pairs the oracle's event list, on every rank."""
+    library's plan, every rank's fixed-point partial forces brought together by one integer all_reduce and its hit pairs
+    by one all_gather.  The sum must be the all-pairs force on every body and the union of the pairs the oracle's
+    event list, on every rank -- the same bits on every rank."""
     import torch.multiprocessing as mp
     mp.spawn(_two_sided_worker, args=(world, _free_port(), n, field, str(tmp_path)), nprocs=world, join=True)
     block = nb.generate(nb.SCENARIO_SQUARE, n, field_w=field, field_h=field)
