@@ -33,7 +33,7 @@ namespace {
 // reference predicate (src/nbody.cu:126-134) -- a hit becomes a candidate of both rows and gives no force
 // (:215-226), anything else gets its force added scalar-wise on both sides.
 //
-// Synchronisation: one mbarrier phase per tile pair (every thread arrives when its rounds are done); the wait
+// Synchronisation: one mbarrier phase per tile pair (every warp arrives when its rounds are done); the wait
 // sits one round into the NEXT tile pair, so warps may drift by a round without stalling.  What follows the wait
 // is everything that needs all warps: the j-side combine of the previous tile pair (double-buffered) and the
 // refill of its ring stage.  Thread 0 is the producer: it walks the queue, writes a descriptor per tile pair
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kSymThreads, SymGeom<IPT>::kMinBlocks) force_s
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        mbar_init(&done_bar, kSymThreads);
+        mbar_init(&done_bar, kSymThreads / 32);   // one arrival per warp: every arrival wakes the warps asleep on the barrier
         fence_barrier_init();
         s_prod.have = 0;
         next_item = fetch();
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(kSymThreads, SymGeom<IPT>::kMinBlocks) force_s
         }
         prevJ = J;
         prev_flags = flags;
-        mbar_arrive(&done_bar);                   // (release) this thread's round results of tile pair t are in place
+        __syncwarp();                             // the lanes' round results of tile pair t are in place ...
+        if (lane == 0) mbar_arrive(&done_bar);    // ... and published by one release per warp
     }
     late(t);                                      // j side of the last tile pair
     if (p.count_stats && lane == 0) {
