@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NB_VERSION 102   /* 102: nb_stats.kernel_launches, nb_probe_fp32; 101: nb_stats / nb_plan grew (two-sided kernel) */
+#define NB_VERSION 103   /* 103: nb_render_grid, nb_plan_warp_item(s), nb_plan_force_scale; 102: nb_stats.kernel_launches, nb_probe_fp32; 101: nb_stats / nb_plan grew (two-sided kernel) */
 
 /* error codes */
 #define NB_OK 0
@@ -217,6 +217,15 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out);
    nb_plan_block_index is its inverse (any order of the two super-tiles).  Host only. */
 int nb_plan_block(int Q, int b, int *R, int *C);
 int nb_plan_block_index(int Q, int X, int Y);
+/* The warp-level two-sided kernel's work items for n bodies with `run` chunks per item: how many ids there are, and which
+   128-row group meets which 64-body chunks [chunk_lo, chunk_hi) under id (group = -1: a void id).  Rank r of W takes ids
+   r, r + W, ...  Host only. */
+int nb_plan_warp_items(int n, int run, int *ids);
+int nb_plan_warp_item(int n, int run, int id, int *group, int *chunk_lo, int *chunk_hi);
+/* The fixed-point scale 2^k of the two-sided kernels' force sums for n bodies with masses <= m_max and radii >= r_min in a
+   field of half-width `field` (n * m_max / (2 r_min)^2 * 2^k < 2^62); NB_ERR_INVALID when no scale leaves 30 bits below a
+   typical force -- the step plan then falls back to the one-sided kernel.  Host only. */
+int nb_plan_force_scale(int n, float m_max, float r_min, int field, int *log2_scale);
 
 /* ---- measurement ---------------------------------------------------------- */
 /*

@@ -34,7 +34,7 @@ UNIQUE_ID_BYTES = 128
 SYMBOLS = [
     "nb_create", "nb_destroy", "nb_last_error", "nb_version", "nb_upload", "nb_download", "nb_num_bodies",
     "nb_step", "nb_step_timed", "nb_step_profile", "nb_sync", "nb_get_stats", "nb_events", "nb_comm_unique_id", "nb_comm_init",
-    "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_render", "nb_render_grid", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
+    "nb_plan_host", "nb_plan_block", "nb_plan_block_index", "nb_plan_warp_items", "nb_plan_warp_item", "nb_plan_force_scale", "nb_render", "nb_render_grid", "nb_write_pgm", "nb_config_parse", "nb_rng_seed", "nb_rng_ival64", "nb_rng_fval",
     "nb_rng_fval_range", "nb_generate", "nb_probe_fp32",
 ]
 
@@ -135,6 +135,9 @@ def lib() -> C.CDLL:
     L.nb_plan_host.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(Plan)]
     L.nb_plan_block.argtypes = [C.c_int, C.c_int, ip, ip]
     L.nb_plan_block_index.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.nb_plan_warp_items.argtypes = [C.c_int, C.c_int, ip]
+    L.nb_plan_warp_item.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip]
+    L.nb_plan_force_scale.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, ip]
     L.nb_render.argtypes = [vp, vp, C.c_int, C.c_int]
     L.nb_render_grid.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.nb_write_pgm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
@@ -197,6 +200,31 @@ def plan_block(Q: int, b: int):
 
 def plan_block_index(Q: int, X: int, Y: int) -> int:
     return lib().nb_plan_block_index(Q, X, Y)
+
+
+def plan_warp_items(n: int, run: int) -> int:
+    """Work-item ids of the warp-level two-sided kernel for n bodies, `run` chunks per item."""
+    ids = C.c_int()
+    rc = lib().nb_plan_warp_items(n, run, C.byref(ids))
+    if rc != OK:
+        raise NbodyError("nb_plan_warp_items", rc, "invalid arguments")
+    return ids.value
+
+
+def plan_warp_item(n: int, run: int, item: int):
+    """(group, chunk_lo, chunk_hi) of a work item, or None for a void id."""
+    g, lo, hi = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().nb_plan_warp_item(n, run, item, C.byref(g), C.byref(lo), C.byref(hi))
+    if rc != OK:
+        raise NbodyError("nb_plan_warp_item", rc, "invalid arguments")
+    return None if g.value < 0 else (g.value, lo.value, hi.value)
+
+
+def plan_force_scale(n: int, m_max: float, r_min: float, field: int):
+    """log2 of the fixed-point scale of the two-sided kernels' force sums, or None when the plan would fall back."""
+    k = C.c_int()
+    rc = lib().nb_plan_force_scale(n, np.float32(m_max), np.float32(r_min), field, C.byref(k))
+    return k.value if rc == OK else None
 
 
 def split(block: np.ndarray, n: int):

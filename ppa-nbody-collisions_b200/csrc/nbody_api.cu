@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -842,6 +843,37 @@ int nb_plan_host(const nb_params *params, int n, int force_grid, nb_plan *out)
     out->sym_Q = d.sym_Q;
     out->sym_blocks = d.sym_blocks;
     out->sym_lgu = d.sym_lgu;
+    return NB_OK;
+}
+
+int nb_plan_warp_items(int n, int run, int *ids)
+{
+    if (n <= 0 || run <= 0 || !ids) return NB_ERR_INVALID;
+    *ids = symw_geom(n, run).ids;
+    return NB_OK;
+}
+
+int nb_plan_warp_item(int n, int run, int id, int *group, int *chunk_lo, int *chunk_hi)
+{
+    if (n <= 0 || run <= 0 || !group || !chunk_lo || !chunk_hi) return NB_ERR_INVALID;
+    const WGeom w = symw_geom(n, run);
+    if (id < 0 || id >= w.ids) return NB_ERR_INVALID;
+    if (!symw_decode(w, id, *group, *chunk_lo, *chunk_hi)) {
+        *group = -1;                               // a void id: no work
+        *chunk_lo = *chunk_hi = 0;
+    }
+    return NB_OK;
+}
+
+int nb_plan_force_scale(int n, float m_max, float r_min, int field, int *log2_scale)
+{
+    if (!log2_scale) return NB_ERR_INVALID;
+    float fscale = 0.f;
+    double finv = 0.0;
+    if (!sym_scale(n, m_max, r_min, field, &fscale, &finv)) return NB_ERR_INVALID;
+    int e = 0;
+    frexpf(fscale, &e);
+    *log2_scale = e - 1;                           // fscale is a power of two: 0.5 * 2^e
     return NB_OK;
 }
 

@@ -224,6 +224,36 @@ __host__ __device__ inline WGeom symw_geom(int n, int run)
     w.ids = 2 * w.G + ((w.G + 1) / 2) * w.L;
     return w;
 }
+// id -> group g and chunk range [c_lo, c_hi); false: a void id
+__host__ __device__ __forceinline__ bool symw_decode(const WGeom &w, int id, int &g, int &c_lo, int &c_hi)
+{
+    if (id < 2 * w.G) {                        // an own item: one chunk
+        g = id >> 1;
+        c_lo = 2 * g + (id & 1);
+        c_hi = min(c_lo + 1, w.C);
+        return c_lo < w.C;
+    }
+    id -= 2 * w.G;
+    const int pi = id / w.L;
+    int off = id - pi * w.L, s;
+    const int s0a = (2 * pi + 2) / w.run, na = max(w.S - s0a, 0);
+    const int gb = w.G - 1 - pi;
+    if (off < na) {
+        g = pi;
+        s = s0a + off;
+    } else {
+        off -= na;
+        if (gb == pi) return false;
+        const int s0b = (2 * gb + 2) / w.run;
+        if (off >= w.S - s0b) return false;       // (also when that row is empty: S - s0b <= 0)
+        g = gb;
+        s = s0b + off;
+    }
+    c_lo = max(s * w.run, 2 * g + 2);
+    c_hi = min((s + 1) * w.run, w.C);
+    return c_lo < c_hi;
+}
+
 // chunks per work item for n bodies on `warps` resident warps: the longest run that still leaves >= 12 items per warp
 __host__ __device__ inline int symw_run(int n, int warps)
 {

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(nb):
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert sorted(nb.SYMBOLS) == declared, "the Python mirror's symbol list is out of date"
-    assert lib.nb_version() == 102
+    assert lib.nb_version() == 103
 
 
 def test_no_cpu_fallback(nb):

@@ -254,3 +254,54 @@ def test_two_sided_deal_and_exchange_equal_the_one_sided_sum(oracle, nb, tmp_pat
         assert np.array_equal(o["pairs"], ev_pairs)
         assert np.array_equal(o["F"], outs[0]["F"]), "ranks disagree on the summed forces"
         assert np.abs(o["F"] - want_F).max() <= 1e-9 * np.abs(want_F).max()
+
+
+def test_warp_level_work_items_cover_the_pair_triangle_once(nb):
+    """Host logic of the warp-level two-sided kernel (nbody_symw.cu): its work-item ids -- the 2 G "own" items first, then
+    the triangle in mirrored row pairs -- decode to (128-row group, run of 64-body chunks) such that every (group, chunk)
+    with chunk >= 2 group is met exactly once, for any run length, and the deal to W ranks (ids r, r + W, ...) is a
+    partition of the same set."""
+    for n in list(range(1, 700, 13)) + [1000, 1024, 5000, 12288, 16384, 16385, 33000, 196607]:
+        for run in (1, 2, 4, 8):
+            if n > 40000 and run < 4:
+                continue                          # (keeps the test fast: 3072 chunks x 1536 groups)
+            G, Cn = (n + 127) // 128, (n + 63) // 64
+            ids = nb.plan_warp_items(n, run)
+            seen = set()
+            owner = {}
+            for item in range(ids):
+                d = nb.plan_warp_item(n, run, item)
+                if d is None:
+                    continue
+                g, lo, hi = d
+                assert 0 <= g < G and 2 * g <= lo < hi <= Cn and hi - lo <= run, (n, run, item, d)
+                if item < 2 * G:
+                    assert (lo >> 1) == g and hi == lo + 1, "the expensive own items have the lowest ids"
+                for c in range(lo, hi):
+                    assert (g, c) not in seen, (n, run, g, c)
+                    seen.add((g, c))
+                    owner[(g, c)] = item % 3
+            assert seen == {(g, c) for g in range(G) for c in range(2 * g, Cn)}, (n, run)
+            if ids >= 30:
+                load = [sum(1 for o in owner.values() if o == r) for r in range(3)]
+                assert min(load) > 0
+    with pytest.raises(nb.NbodyError):
+        nb.plan_warp_item(1000, 1, nb.plan_warp_items(1000, 1))
+
+
+def test_fixed_point_scale_of_the_force_sums(nb):
+    """The scale 2^k of the two-sided kernels' 64-bit force sums: n m_max / (2 r_min)^2 * 2^k stays below 2^62 (no body's
+    |F| can overflow), one unit is at least 30 bits below a typical force, and radii too small for that make the plan
+    fall back to the one-sided kernel instead."""
+    for n, m_max, r_min, field in ((1 << 20, 1e17, 50.0, 800000), (16384, 1e17, 50.0, 100000), (1 << 22, 3e18, 50.0, 3000000),
+                                   (131072, 1e17, 50.0, 200000), (2000, 1.0, 1.0, 10)):
+        k = nb.plan_force_scale(n, m_max, r_min, field)
+        assert k is not None
+        bound = n * float(np.float32(m_max)) / (4.0 * float(np.float32(r_min)) ** 2)
+        assert bound * 2.0 ** k < 2.0 ** 62 and bound * 2.0 ** (k + 2) >= 2.0 ** 62, (n, k)
+        typical = n * 0.5 * m_max / float(field) ** 2           # a body inside a disc of the field's size
+        assert typical * 2.0 ** k >= 2.0 ** 29, "one unit must be far below a typical force"
+    assert nb.plan_force_scale(1 << 20, 1e17, 0.0, 800000) is None          # r_min = 0: no bound on |F|
+    assert nb.plan_force_scale(1 << 20, 1e17, 1.0, 800000) is None          # radii tiny against the field: too coarse
+    assert nb.plan_force_scale(0, 1e17, 50.0, 800000) is None
+    assert nb.plan_force_scale(1 << 20, 0.0, 50.0, 800000) is None
